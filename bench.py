@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- depth-filter frames/sec on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[1] -- a 640x480 synthetic pinhole
+sequence, 200 frames, 5x5 NCC, one reference keyframe per GPU.  A *step* is one
+pass of the hot path over one such sequence: setReferenceImage on frame 0, then
+199 fused depth-filter updates (check + epipolar NCC search + triangulation +
+Bayesian update).  frames/sec counts the 199 update() frames, the protocol of
+the reference's test/dataset_main.cpp:101-105.
+
+  value   whole-job frames/s with the 200 frames already resident in HBM
+          (246 MB of distinct frames per step, > the 126 MB L2, streamed once
+          per step; the 13.5 MB seed state is legitimately L2-resident from one
+          frame to the next -- that is the workload, not a cached input);
+  e2e     the same metric through the reference-facing host API
+          (SeedMatrix::setReferenceImage / update with HOST float buffers ->
+          pinned ring -> H2D inside the timed region, final depth + convergence
+          maps read back to the host every step);
+  N > 1   independent keyframes, one per rank (weak scaling), NCCL only for the
+          final gather of the depth and convergence maps to rank 0.
+
+`--impl reference` runs the reference's own implementation of the path instead:
+its unmodified CUDA kernels rebuilt for sm_100a (oracle/_ref/librmd_ref.so,
+recipe oracle/Makefile) through rmd::SeedMatrix with host buffers, when that
+library and a GPU are present; otherwise the CPU oracle port.  (The reference
+has no CPU implementation of the path; its "dataset_main" drives CUDA kernels:
+SURVEY.md, first table.)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "depth-filter frames/sec (VGA, 200-frame seq)"
+UNIT = "frames/s"
+BYTES_PER_PIXEL_FUSED = 52  # SURVEY.md 8d / BASELINE.md 4: algorithmic bytes per pixel per frame
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--patch", type=int, default=5)
+    ap.add_argument("--variant", default=None, choices=[None, "staged", "direct"])
+    ap.add_argument("--cpu-frames", type=int, default=6,
+                    help="bounded sample of the sequence for the CPU baseline (frames 1..n)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-cpu", action="store_true",
+                    help="--impl reference: force the CPU oracle port even if the reference CUDA build exists")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ helpers
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_sequence(args, rank):
+    """Renders the rank's synthetic sequence on the host (float32 frames,
+    uint8-quantised like the reference's MONO8 input, src/depthmap.cpp:105)."""
+    from rpg_open_remode_b200 import synth
+    seq = synth.SyntheticSequence(args.width, args.height, seed=0x5EED0002 + 16 * rank)
+    n = args.frames
+    frames = np.empty((n, args.height, args.width), np.float32)
+    poses = np.empty((n, 12), np.float32)   # T_curr_world (world -> camera)
+    depth0 = None
+    for k in range(n):
+        f = seq.frame(k, want_depth=(k == 0))
+        frames[k] = f.image
+        poses[k] = f.T_cam_world.reshape(12)
+        if k == 0:
+            depth0 = f.depth
+    return seq, frames, poses, float(depth0.min()), float(depth0.max())
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(args, frames, poses, dmin, dmax, seq):
+    """CPU oracle port (oracle/librmd_oracle.so, OpenMP, all host threads) timed
+    on a bounded sample of the same workload: frames 1..n of the sequence."""
+    import oracle_binding as ob
+    n = max(1, min(args.cpu_frames, args.frames - 1))
+    threads = ob.get_threads()
+    o = ob.OracleSeeds(args.width, args.height, *seq.camera, patch=args.patch)
+    o.set_reference(frames[0], poses[0], dmin, dmax)
+    t0 = time.perf_counter()
+    for k in range(1, n + 1):
+        o.update(frames[k], poses[k])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"frames 1..{n} of the {args.width}x{args.height} sequence (the search-heavy start), "
+                      f"{dt:.1f} s wall, OpenMP over image rows"}
+
+
+# ------------------------------------------------------------------- ours
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import rpg_open_remode_b200 as rmd
+
+    if not torch.cuda.is_available() or rmd.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    seq, frames, poses, dmin, dmax = load_sequence(args, rank)
+    W, H, NF = args.width, args.height, args.frames
+    n_upd = NF - 1
+
+    seeds = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera), patch_side=args.patch, device=local_rank)
+    variant = args.variant or os.environ.get("RMD_BENCH_VARIANT", "staged")
+    seeds.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED if variant == "staged" else rmd.VARIANT_DIRECT)
+    stream = torch.cuda.current_stream(dev)
+    seeds.setStream(stream.cuda_stream)
+
+    # frames resident in HBM for `value`; pinned host frames for `e2e`
+    host_frames = torch.from_numpy(frames).pin_memory()
+    dev_frames = host_frames.to(dev, non_blocking=False)
+    frame_bytes = W * H * 4
+    depth_out = torch.empty((H, W), dtype=torch.float32, device=dev)
+    conv_out = torch.empty((H, W), dtype=torch.int32, device=dev)
+    gather_depth = [torch.empty_like(depth_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gather_conv = [torch.empty_like(conv_out) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def final_gather():
+        # the only collective on the path: final depth + convergence maps to rank 0 (NCCL)
+        seeds.copyFieldToDevice(rmd.FIELD_MU, depth_out.data_ptr(), W * 4)
+        seeds.copyFieldToDevice(rmd.FIELD_CONVERGENCE, conv_out.data_ptr(), W * 4)
+        if world > 1:
+            dist.gather(depth_out, gather_depth, dst=0)
+            dist.gather(conv_out, gather_conv, dst=0)
+
+    def step_resident():
+        seeds.setReferenceImageDevice(dev_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)
+        seeds.updateDeviceBatch(dev_frames[1].data_ptr(), frame_bytes, W * 4, poses[1:])
+        final_gather()
+
+    def step_e2e():
+        seeds.setReferenceImage(frames[0], poses[0], dmin, dmax)
+        for k in range(1, NF):
+            seeds.update(frames[k], poses[k])
+        final_gather()
+        # device -> host read of the step's result (final maps of this rank)
+        d = depth_out.cpu()
+        c = conv_out.cpu()
+        return d, c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    # ---------------- device-resident timing (value)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = seeds.launchCount()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches1 = seeds.launchCount()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n_upd * args.steps / (dev_ms * 1e-3)
+    ms_per_step = dev_ms / args.steps
+
+    # ---------------- per-launch duration of the dominant kernel (roofline)
+    # one more identical step with a CUDA-event pair around every fused launch
+    seeds.setReferenceImageDevice(dev_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_upd)]
+    for k in range(1, NF):
+        a, b = evs[k - 1]
+        a.record(stream)
+        seeds.updateDevice(dev_frames[k].data_ptr(), W * 4, poses[k])
+        b.record(stream)
+    torch.cuda.synchronize(dev)
+    per_launch_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    conv_hist = np.bincount(seeds.downloadConvergence().ravel(), minlength=6).tolist()
+    avg_launch_s = float(per_launch_ms.mean()) * 1e-3
+    algo_bytes = BYTES_PER_PIXEL_FUSED * W * H
+    peak, peak_src = peaks()
+    achieved = algo_bytes / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "depth_filter_%s_kernel<%d>" % (variant, args.patch),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "avg_launch_us": avg_launch_s * 1e6,
+                "launch_us_min_median_max": [float(per_launch_ms.min() * 1e3), float(np.median(per_launch_ms) * 1e3),
+                                             float(per_launch_ms.max() * 1e3)],
+                "kernel_share_of_step": float(per_launch_ms.sum() / ms_per_step),
+                "note": "search-heavy frames are FP32-issue / shared-memory bound (<=143 candidates x 25 bilinear "
+                        "taps per seed), not HBM bound: see DESIGN.md 'Roofline'"}
+
+    # ---------------- end-to-end timing through the host API (e2e)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * n_upd * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(NF * frame_bytes), "d2h_bytes_per_step": int(2 * frame_bytes),
+           "ms_per_step": e2e_s * 1e3 / args.steps}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{W}x{H} synthetic pinhole sequence, {NF} frames ({n_upd} updates), "
+                               f"{args.patch}x{args.patch} NCC, 1 reference keyframe per GPU (BASELINE configs[1])",
+                   "parallelism": f"{world} independent keyframes, NCCL gather of final depth+convergence",
+                   "kernel_variant": variant,
+                   "l2": "inputs larger than L2: 200 distinct frames = %.0f MB streamed per step; seed state "
+                         "(%.1f MB) is L2-resident by design" % (NF * frame_bytes / 1e6, 28 * W * H / 1e6),
+                   "final_state_hist[update,converged,border,diverged,no_match,not_visible]": conv_hist},
+        "e2e": e2e, "roofline": roofline,
+        "gpu_launches": int((launches1[1] - launches0[1])),
+        "gpu_launches_fused": int((launches1[0] - launches0[0])),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, frames, poses, dmin, dmax, seq)
+    return out
+
+
+# -------------------------------------------------------------- reference
+
+def run_reference(args, rank, world, local_rank):
+    """The reference's own path on this box.  Rank 0 alone runs it."""
+    if rank != 0:
+        return None
+    import ref_binding as rb
+    seq, frames, poses, dmin, dmax = load_sequence(args, 0)
+    W, H, NF = args.width, args.height, args.frames
+    n_upd = NF - 1
+    frame_bytes = W * H * 4
+    use_cuda = False
+    if not args.reference_cpu and rb.available(args.patch):
+        try:
+            use_cuda = rb.lib(args.patch).ref_device_count() > 0
+        except OSError:
+            use_cuda = False
+    base_cfg = {"workload": f"{W}x{H} synthetic pinhole sequence, {NF} frames ({n_upd} updates), "
+                            f"{args.patch}x{args.patch} NCC, 1 reference keyframe (BASELINE configs[1])"}
+    if use_cuda:
+        ref = rb.RefSeeds(W, H, *seq.camera, patch=args.patch)
+
+        def step():
+            ref.set_reference(frames[0], poses[0], dmin, dmax)
+            for k in range(1, NF):
+                ref.update(frames[k], poses[k])
+            ref.sync()
+            return ref.download(0), ref.download(4)
+
+        for _ in range(args.warmup):
+            step()
+        sampler = ClockSampler(0)
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        v = n_upd * args.steps / dt
+        return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": base_cfg,
+                "cpu_baseline": {"value": v, "unit": UNIT, "kind": "reference", "cores": 1,
+                                 "sample": "whole workload; NOTE the reference has no CPU implementation of this "
+                                           "path -- this is its unmodified CUDA path (src/seed_matrix.cu and its "
+                                           "kernels) rebuilt for sm_100a with texture objects "
+                                           "(oracle/Makefile), 1 host thread driving 1 GPU, host float frames in, "
+                                           "sync pageable H2D per frame as the reference does"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(NF * frame_bytes),
+                        "d2h_bytes_per_step": int(2 * frame_bytes)},
+                "clocks": clocks}
+    # CPU oracle port, bounded sample per step
+    import oracle_binding as ob
+    n = max(1, min(args.cpu_frames, n_upd))
+    o = ob.OracleSeeds(W, H, *seq.camera, patch=args.patch)
+
+    def step_cpu():
+        o.set_reference(frames[0], poses[0], dmin, dmax)
+        for k in range(1, n + 1):
+            o.update(frames[k], poses[k])
+
+    for _ in range(min(args.warmup, 1)):
+        step_cpu()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_cpu()
+    dt = time.perf_counter() - t0
+    v = n * steps / dt
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3 / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
+            "cpu_baseline": {"value": v, "unit": UNIT, "kind": "port", "cores": ob.get_threads(),
+                             "sample": f"frames 1..{n} of the sequence per step (search-heavy start), OpenMP"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world, local_rank)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local_rank))
+    out = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

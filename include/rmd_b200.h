@@ -1,0 +1,243 @@
+/*
+ * rmd_b200.h -- C-ABI of the Blackwell-native REMODE depth-filter hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ types, no
+ * exceptions, no torch.  Every entry point replaces one member of the
+ * reference's device-side classes (paths relative to the reference tree):
+ *
+ *   rmd_seeds_*      rmd::SeedMatrix        include/rmd/seed_matrix.cuh:45-109
+ *                                           src/seed_matrix.cu:28-230
+ *   rmd_denoiser_*   rmd::DepthmapDenoiser  include/rmd/depthmap_denoiser.cuh:27-54
+ *                                           src/depthmap_denoiser.cu:124-229
+ *   rmd_reduce_*     rmd::ImageReducer<T>   include/rmd/reduction.cuh:27-62
+ *                                           src/reduction.cu:22-187
+ *   rmd_image_*      rmd::DeviceImage<T>    include/rmd/device_image.cuh:34-180
+ *
+ * include/rmd/ holds header-compatible C++ classes (same names and signatures
+ * as the reference's) that forward to these functions and turn non-zero
+ * return codes back into rmd::CudaException, so rmd::Depthmap / the ROS node
+ * compile against them unchanged.
+ *
+ * Conventions
+ *   - every function returns 0 on success, otherwise a cudaError_t value or
+ *     one of the RMD_ERR_* codes below; rmd_last_error_string() describes the
+ *     last failure of the calling thread;
+ *   - host images are densely packed row-major (width*sizeof(T) pitch), gray
+ *     value / 255 in [0,1] for float frames, as the reference requires
+ *     (device_image.cuh:95-102, src/depthmap.cpp:105);
+ *   - poses are SE3 3x4 row-major [R|t] float[12] (include/rmd/se3.cuh:27-142),
+ *     world -> camera ("T_curr_world"), exactly what SeedMatrix takes;
+ *   - a handle owns its device memory and a CUDA stream on the device it was
+ *     created for; handles share no process-global state, so several can run
+ *     concurrently on one GPU or one per GPU;
+ *   - calls on one handle must come from one thread at a time (as with the
+ *     reference: src/main_ros.cpp:43-48).
+ */
+#ifndef RMD_B200_H
+#define RMD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMD_B200_ABI_VERSION 1
+
+/* own error codes (cudaError_t values are small positive integers) */
+#define RMD_ERR_INVALID_ARGUMENT (-1)
+#define RMD_ERR_NOT_INITIALISED  (-2)  /* e.g. update before set_reference */
+#define RMD_ERR_UNSUPPORTED      (-3)
+
+/* rmd::ConvergenceStates, include/rmd/seed_matrix.cuh:31-43 */
+enum rmd_convergence_state {
+  RMD_UPDATE = 0,
+  RMD_CONVERGED = 1,
+  RMD_BORDER = 2,
+  RMD_DIVERGED = 3,
+  RMD_NO_MATCH = 4,
+  RMD_NOT_VISIBLE = 5
+};
+
+/* Per-pixel fields of a seed matrix (download / upload / device_ptr). */
+enum rmd_field {
+  RMD_FIELD_MU = 0,                /* float   SeedMatrix::downloadDepthmap    seed_matrix.cu:160 */
+  RMD_FIELD_SIGMA_SQ = 1,          /* float   downloadSigmaSq                 :206 */
+  RMD_FIELD_A = 2,                 /* float   downloadA                       :210 */
+  RMD_FIELD_B = 3,                 /* float   downloadB                       :214 */
+  RMD_FIELD_CONVERGENCE = 4,       /* int32   downloadConvergence             :165 */
+  RMD_FIELD_SUM_TEMPL = 5,         /* float   downloadSumTempl                :218 */
+  RMD_FIELD_CONST_TEMPL_DENOM = 6, /* float   downloadConstTemplDenom         :222 */
+  RMD_FIELD_EPIPOLAR_MATCHES = 7,  /* float2  downloadEpipolarMatches         :226 */
+  RMD_FIELD_REF_IMG = 8            /* float   the reference image as uploaded */
+};
+
+enum rmd_seeds_option {
+  /* 1: keep the best epipolar match of every pixel (RMD_FIELD_EPIPOLAR_MATCHES);
+   * off by default because nothing downstream of update() reads it
+   * (it exists in the reference for tests: seed_matrix.cuh:76-83). */
+  RMD_OPT_RECORD_MATCHES = 0,
+  /* 0: staged kernel (TMA -> shared memory, balanced candidate work list),
+   * 1: direct kernel (one thread per pixel, global loads); same arithmetic. */
+  RMD_OPT_KERNEL_VARIANT = 1,
+  /* fractional bits of the bilinear weights of the current-image taps
+   * (8 = what the texture unit of the reference path uses; 0 = exact fp32). */
+  RMD_OPT_TEX_FRAC_BITS = 2
+};
+
+typedef struct rmd_seeds rmd_seeds_t;
+typedef struct rmd_denoiser rmd_denoiser_t;
+
+/* ------------------------------------------------------------------ misc */
+int rmd_abi_version(void);
+const char *rmd_last_error_string(void);
+int rmd_device_count(int *count);
+
+/* ----------------------------------------------------------- seed matrix */
+
+/* SeedMatrix::SeedMatrix(width, height, PinholeCamera(fx,fy,cx,cy))
+ * seed_matrix.cu:28-80.  patch_side = RMD_CORR_PATCH_SIDE (5 or 7; a compile
+ * time macro in the reference, CMakeLists.txt:51).  device < 0: current. */
+int rmd_seeds_create(int width, int height, float fx, float fy, float cx,
+                     float cy, int patch_side, int device, rmd_seeds_t **out);
+int rmd_seeds_destroy(rmd_seeds_t *s);
+
+/* Run this handle's work on a caller-owned cudaStream_t (NULL = back to the
+ * handle's own stream).  The reference uses the legacy default stream only. */
+int rmd_seeds_set_stream(rmd_seeds_t *s, void *cuda_stream);
+int rmd_seeds_get_stream(rmd_seeds_t *s, void **cuda_stream);
+int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value);
+
+/* SeedMatrix::setReferenceImage, seed_matrix.cu:87-118.  Host buffer. */
+int rmd_seeds_set_reference(rmd_seeds_t *s, const float *host_img,
+                            const float *T_curr_world, float min_depth,
+                            float max_depth);
+/* Same with the image already in device memory (pitch in bytes). */
+int rmd_seeds_set_reference_device(rmd_seeds_t *s, const float *dev_img,
+                                   size_t pitch_bytes,
+                                   const float *T_curr_world, float min_depth,
+                                   float max_depth);
+/* Same from an 8-bit gray frame; value * (1/255.f) is applied on the GPU
+ * (what rmd::Depthmap::inputImage does on the CPU, src/depthmap.cpp:105). */
+int rmd_seeds_set_reference_u8(rmd_seeds_t *s, const uint8_t *host_img,
+                               const float *T_curr_world, float min_depth,
+                               float max_depth);
+
+/* SeedMatrix::update, seed_matrix.cu:120-158: convergence check, epipolar NCC
+ * search, triangulation and Bayesian update of every seed -- one fused kernel.
+ * The host buffer may be reused as soon as the call returns (it is copied to
+ * a pinned ring); the GPU work is enqueued on the handle's stream and, like
+ * the reference's last kernel, may still be running on return. */
+int rmd_seeds_update(rmd_seeds_t *s, const float *host_img,
+                     const float *T_curr_world);
+int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img,
+                        const float *T_curr_world);
+/* Frame already resident in device memory (must stay valid until the stream
+ * has consumed it).  pitch_bytes must be a multiple of 16. */
+int rmd_seeds_update_device(rmd_seeds_t *s, const float *dev_img,
+                            size_t pitch_bytes, const float *T_curr_world);
+
+/* n_frames consecutive updates from frames resident in device memory:
+ * frame i starts at dev_frames + i*frame_stride_bytes (pitch_bytes per row),
+ * its pose is T_curr_world + 12*i.  One call, n_frames fused launches, no
+ * host round trip in between (the sequence is strictly ordered: frame k+1
+ * searches around the posterior frame k left, epipolar_match.cu:60-75). */
+int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames,
+                                  size_t frame_stride_bytes,
+                                  size_t pitch_bytes, int n_frames,
+                                  const float *T_curr_world);
+
+int rmd_seeds_sync(rmd_seeds_t *s);
+
+/* download* accessors: dst is width*height elements, densely packed. */
+int rmd_seeds_download(rmd_seeds_t *s, int field, void *host_dst);
+/* Test / checkpoint hook the reference lacks: overwrite one field
+ * (MU, SIGMA_SQ, A, B, CONVERGENCE). */
+int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src);
+/* getMu()/getSigmaSq()/getA()/getB()/getConvergence(): a pitched planar
+ * device image of the field, valid until the next call on this handle. */
+int rmd_seeds_device_ptr(rmd_seeds_t *s, int field, void **dev_ptr,
+                         size_t *pitch_bytes);
+/* Copy a field into caller-owned device memory on the handle's stream. */
+int rmd_seeds_copy_field_to_device(rmd_seeds_t *s, int field, void *dev_dst,
+                                   size_t dst_pitch_bytes);
+
+/* SeedMatrix::getConvergedCount, seed_matrix.cu:195-198: number of pixels the
+ * last update() classified CONVERGED (the fused kernel counts them; no extra
+ * pass).  Before the first update it is 0. */
+int rmd_seeds_converged_count(rmd_seeds_t *s, size_t *count);
+/* SeedMatrix::getDistFromRef, seed_matrix.cu:200-203. */
+int rmd_seeds_dist_from_ref(rmd_seeds_t *s, float *dist);
+int rmd_seeds_size(rmd_seeds_t *s, int *width, int *height, int *patch_side);
+/* Number of fused depth-filter kernels / all kernels this handle launched. */
+int rmd_seeds_launch_count(rmd_seeds_t *s, uint64_t *fused, uint64_t *total);
+/* Device time of the last fused depth-filter kernel in milliseconds, measured
+ * with CUDA events on the handle's stream (blocks until it finished). */
+int rmd_seeds_last_kernel_ms(rmd_seeds_t *s, float *ms);
+int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on);
+
+/* -------------------------------------------------------------- denoiser */
+
+/* DepthmapDenoiser(width, height), depthmap_denoiser.cu:143-177 */
+int rmd_denoiser_create(int width, int height, int device,
+                        rmd_denoiser_t **out);
+int rmd_denoiser_destroy(rmd_denoiser_t *d);
+int rmd_denoiser_set_stream(rmd_denoiser_t *d, void *cuda_stream);
+/* setLargeSigmaSq(depth_range), :226-229 */
+int rmd_denoiser_set_large_sigma_sq(rmd_denoiser_t *d, float depth_range);
+/* denoise(mu, sigma_sq, a, b, host_denoised, lambda, iterations), :179-224.
+ * Inputs are pitched planar float images in device memory (pitch in bytes).
+ * Returns RMD_ERR_NOT_INITIALISED if set_large_sigma_sq was never called
+ * (the reference prints to stderr and returns, :189-193). */
+int rmd_denoiser_run(rmd_denoiser_t *d, const float *mu, size_t mu_pitch,
+                     const float *sigma_sq, size_t sigma_sq_pitch,
+                     const float *a, size_t a_pitch, const float *b,
+                     size_t b_pitch, float *host_denoised, float lambda,
+                     int iterations);
+/* Same, reading the seed state of `s` directly (no planar export). */
+int rmd_denoiser_run_seeds(rmd_denoiser_t *d, rmd_seeds_t *s,
+                           float *host_denoised, float lambda, int iterations);
+/* Same, leaving the result in caller-owned device memory (no D2H copy). */
+int rmd_denoiser_run_seeds_to_device(rmd_denoiser_t *d, rmd_seeds_t *s,
+                                     float *dev_out, size_t out_pitch_bytes,
+                                     float lambda, int iterations);
+int rmd_denoiser_sync(rmd_denoiser_t *d);
+int rmd_denoiser_launch_count(rmd_denoiser_t *d, uint64_t *total);
+
+/* ------------------------------------------------------------ reductions */
+
+/* ImageReducer<T>::sum / countEqual, reduction.cu:81-184.  Device pointer,
+ * stride in ELEMENTS (as the reference), legacy default stream, blocking. */
+int rmd_reduce_sum_f32(const float *dev_img, size_t stride, size_t width,
+                       size_t height, float *out);
+int rmd_reduce_sum_i32(const int32_t *dev_img, size_t stride, size_t width,
+                       size_t height, int32_t *out);
+int rmd_reduce_count_eq_i32(const int32_t *dev_img, size_t stride,
+                            size_t width, size_t height, int32_t value,
+                            size_t *out);
+/* extras the north star asks for (not in the reference) */
+int rmd_reduce_min_max_f32(const float *dev_img, size_t stride, size_t width,
+                           size_t height, float *out_min, float *out_max);
+
+/* ---------------------------------------------------------- device image */
+
+/* DeviceImage<T>(width,height) = cudaMallocPitch, device_image.cuh:37-50 */
+int rmd_image_alloc(size_t width, size_t height, size_t elem_size,
+                    void **dev_ptr, size_t *pitch_bytes);
+int rmd_image_free(void *dev_ptr);
+/* setDevData / getDevData / zero / operator=, device_image.cuh:93-171 */
+int rmd_image_upload(void *dev_ptr, size_t pitch_bytes, const void *host_src,
+                     size_t width, size_t height, size_t elem_size);
+int rmd_image_download(const void *dev_ptr, size_t pitch_bytes, void *host_dst,
+                       size_t width, size_t height, size_t elem_size);
+int rmd_image_zero(void *dev_ptr, size_t pitch_bytes, size_t width,
+                   size_t height, size_t elem_size);
+int rmd_image_copy(void *dst, size_t dst_pitch, const void *src,
+                   size_t src_pitch, size_t width, size_t height,
+                   size_t elem_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMD_B200_H */

@@ -1,0 +1,1126 @@
+// c_api.cu -- the C-ABI (include/rmd_b200.h): handles, host sequencing, copies.
+//
+// Host-side counterpart of rmd::SeedMatrix (src/seed_matrix.cu),
+// rmd::DepthmapDenoiser (src/depthmap_denoiser.cu:143-229),
+// rmd::ImageReducer (src/reduction.cu) and rmd::DeviceImage
+// (include/rmd/device_image.cuh), re-designed: per-handle streams instead of
+// the legacy default stream, a pinned upload ring with a copy stream so the
+// H2D transfer of frame k+1 overlaps the kernel of frame k, one fused launch
+// per frame and no device synchronisation inside update().
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "denoiser.cuh"
+#include "depth_filter.cuh"
+#include "reduction.cuh"
+#include "rmd_common.cuh"
+#include "staged_maps.cuh"
+
+namespace rmdb
+{
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string t_last_error;
+
+void set_last_error(const std::string &msg) { t_last_error = msg; }
+
+int fail(int code, const char *what)
+{
+  t_last_error = what;
+  return code;
+}
+
+int fail_cuda(cudaError_t err, const char *what)
+{
+  t_last_error = std::string(what) + ": " + cudaGetErrorName(err) + " (" +
+                 cudaGetErrorString(err) + ")";
+  cudaGetLastError();  // clear the sticky-less error state
+  return (int)err;
+}
+
+// ---------------------------------------------------------------- geometry
+Pose pose_inverse(const Pose &T)
+{
+  Pose r;
+  const float *d = T.m;
+  r.m[0] = d[0]; r.m[1] = d[4]; r.m[2] = d[8];
+  r.m[4] = d[1]; r.m[5] = d[5]; r.m[6] = d[9];
+  r.m[8] = d[2]; r.m[9] = d[6]; r.m[10] = d[10];
+  r.m[3] = -d[0] * d[3] - d[4] * d[7] - d[8] * d[11];
+  r.m[7] = -d[1] * d[3] - d[5] * d[7] - d[9] * d[11];
+  r.m[11] = -d[2] * d[3] - d[6] * d[7] - d[10] * d[11];
+  return r;
+}
+
+Pose pose_compose(const Pose &A, const Pose &B)
+{
+  Pose r;
+  for(int row = 0; row < 3; ++row)
+  {
+    const float *a = A.m + 4 * row;
+    for(int col = 0; col < 3; ++col)
+      r.m[4 * row + col] = a[0] * B.m[col] + a[1] * B.m[4 + col] + a[2] * B.m[8 + col];
+    r.m[4 * row + 3] = a[3] + a[0] * B.m[3] + a[1] * B.m[7] + a[2] * B.m[11];
+  }
+  return r;
+}
+
+static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+} // namespace rmdb
+
+using namespace rmdb;
+
+// =========================================================== seed matrix
+
+static const int kSlots = 3;
+
+struct rmd_seeds
+{
+  int device;
+  int width, height, patch;
+  Camera cam;
+  float one_pix_angle;
+
+  cudaStream_t own_stream, stream, copy_stream;
+
+  float4 *seed; int seed_stride;
+  float2 *templ; int templ_stride;
+  int *conv; size_t conv_pitch;
+  float *ref; size_t ref_pitch;
+  float *curr[kSlots]; size_t curr_pitch;
+  uint8_t *curr_u8[kSlots]; size_t curr_u8_pitch;
+  void *pinned[kSlots];
+  cudaEvent_t copied[kSlots], consumed[kSlots];
+  bool slot_used[kSlots];
+  int next_slot;
+
+  float2 *matches; size_t matches_pitch;
+  float *planar[6]; size_t planar_pitch;   // mu, sigma_sq, a, b, sum_templ, denom
+  float *dense_tmp;                        // width*height floats, uploads/downloads
+  unsigned int *counters;                  // 2 x converged count
+
+  // scene / algorithm parameters (src/seed_matrix.cu:96-104)
+  float min_depth, max_depth, avg_depth, depth_range, sigma_sq_max;
+  float eta_inlier, eta_outlier, epsilon;
+  Pose T_world_ref;
+  float dist_from_ref;
+  bool has_reference;
+  uint64_t frame_index;   // number of updates since set_reference
+  bool trust_conv;
+
+  bool record_matches;
+  int variant;            // 0 staged, 1 direct
+  int tex_frac_bits;
+
+  uint64_t n_fused, n_total;
+  bool timing;
+  cudaEvent_t t0, t1;
+  bool t_valid;
+
+  StagedMaps *maps;
+};
+
+namespace
+{
+
+int seeds_alloc(rmd_seeds *s)
+{
+  const int w = s->width, h = s->height;
+  RMD_CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  RMD_CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  s->stream = s->own_stream;
+  s->seed_stride = (int)round_up(w, 32);
+  s->templ_stride = (int)round_up(w, 32);
+  RMD_CUDA_TRY(cudaMalloc(&s->seed, sizeof(float4) * (size_t)s->seed_stride * h));
+  RMD_CUDA_TRY(cudaMalloc(&s->templ, sizeof(float2) * (size_t)s->templ_stride * h));
+  RMD_CUDA_TRY(cudaMallocPitch(&s->conv, &s->conv_pitch, sizeof(int) * (size_t)w, h));
+  RMD_CUDA_TRY(cudaMallocPitch(&s->ref, &s->ref_pitch, sizeof(float) * (size_t)w, h));
+  for(int i = 0; i < kSlots; ++i)
+  {
+    RMD_CUDA_TRY(cudaMallocPitch(&s->curr[i], &s->curr_pitch, sizeof(float) * (size_t)w, h));
+    RMD_CUDA_TRY(cudaHostAlloc(&s->pinned[i], sizeof(float) * (size_t)w * h, cudaHostAllocDefault));
+    RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
+    RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
+  }
+  RMD_CUDA_TRY(cudaMalloc(&s->counters, 2 * sizeof(unsigned int)));
+  RMD_CUDA_TRY(cudaMemset(s->counters, 0, 2 * sizeof(unsigned int)));
+  RMD_CUDA_TRY(cudaMemset2D(s->conv, s->conv_pitch, 0, sizeof(int) * (size_t)w, h));
+  RMD_CUDA_TRY(cudaEventCreate(&s->t0));
+  RMD_CUDA_TRY(cudaEventCreate(&s->t1));
+  return 0;
+}
+
+void seeds_free(rmd_seeds *s)
+{
+  cudaDeviceSynchronize();
+  if(s->own_stream) cudaStreamDestroy(s->own_stream);
+  if(s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  cudaFree(s->seed); cudaFree(s->templ); cudaFree(s->conv); cudaFree(s->ref);
+  for(int i = 0; i < kSlots; ++i)
+  {
+    cudaFree(s->curr[i]);
+    cudaFree(s->curr_u8[i]);
+    if(s->pinned[i]) cudaFreeHost(s->pinned[i]);
+    if(s->copied[i]) cudaEventDestroy(s->copied[i]);
+    if(s->consumed[i]) cudaEventDestroy(s->consumed[i]);
+  }
+  cudaFree(s->matches);
+  for(int i = 0; i < 6; ++i) cudaFree(s->planar[i]);
+  cudaFree(s->dense_tmp);
+  cudaFree(s->counters);
+  if(s->t0) cudaEventDestroy(s->t0);
+  if(s->t1) cudaEventDestroy(s->t1);
+  delete s->maps;
+  cudaGetLastError();
+}
+
+int ensure_dense_tmp(rmd_seeds *s)
+{
+  if(!s->dense_tmp)
+    RMD_CUDA_TRY(cudaMalloc(&s->dense_tmp, sizeof(float) * 2 * (size_t)s->width * s->height));
+  return 0;
+}
+
+int ensure_matches(rmd_seeds *s)
+{
+  if(!s->matches)
+  {
+    RMD_CUDA_TRY(cudaMallocPitch(&s->matches, &s->matches_pitch, sizeof(float2) * (size_t)s->width,
+                                 s->height));
+    RMD_CUDA_TRY(cudaMemset2DAsync(s->matches, s->matches_pitch, 0,
+                                   sizeof(float2) * (size_t)s->width, s->height, s->stream));
+  }
+  return 0;
+}
+
+// Run the seed-initialisation kernel on the reference image now in s->ref.
+int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_depth, float max_depth)
+{
+  s->min_depth = min_depth;
+  s->max_depth = max_depth;
+  s->avg_depth = (min_depth + max_depth) / 2.0f;
+  s->depth_range = max_depth - min_depth;
+  s->sigma_sq_max = s->depth_range * s->depth_range / 36.0f;
+  s->eta_inlier = 0.7f;
+  s->eta_outlier = 0.05f;
+  s->epsilon = s->depth_range / 1000.0f;
+  s->T_world_ref = pose_inverse(pose_from(T_curr_world));
+
+  InitParams ip;
+  ip.width = s->width; ip.height = s->height;
+  ip.ref = s->ref; ip.ref_stride = (int)(s->ref_pitch / sizeof(float));
+  ip.seed = s->seed; ip.seed_stride = s->seed_stride;
+  ip.templ = s->templ; ip.templ_stride = s->templ_stride;
+  ip.conv = s->conv; ip.conv_stride = (int)(s->conv_pitch / sizeof(int));
+  ip.avg_depth = s->avg_depth; ip.sigma_sq_max = s->sigma_sq_max;
+  RMD_CUDA_TRY(launch_seed_init(ip, s->patch, s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned int), s->stream));
+  s->n_total += 1;
+  s->has_reference = true;
+  s->frame_index = 0;
+  s->trust_conv = true;
+  s->dist_from_ref = 0.0f;
+  return 0;
+}
+
+// Enqueue the fused depth-filter kernel for the frame at (curr, pitch).
+int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const float *T_curr_world)
+{
+  const Pose T_curr_ref = pose_compose(pose_from(T_curr_world), s->T_world_ref);  // seed_matrix.cu:124
+  const float tx = T_curr_ref.m[3], ty = T_curr_ref.m[7], tz = T_curr_ref.m[11];
+  s->dist_from_ref = sqrtf(tx * tx + ty * ty + tz * tz);                          // :125
+
+  s->frame_index += 1;
+  FilterParams P;
+  memset(&P, 0, sizeof(P));
+  P.width = s->width; P.height = s->height;
+  P.seed = s->seed; P.seed_stride = s->seed_stride;
+  P.templ = s->templ; P.templ_stride = s->templ_stride;
+  P.conv = s->conv; P.conv_stride = (int)(s->conv_pitch / sizeof(int));
+  P.ref = s->ref; P.ref_stride = (int)(s->ref_pitch / sizeof(float));
+  P.curr = curr; P.curr_stride = (int)(curr_pitch / sizeof(float));
+  if(s->record_matches)
+  {
+    const int rc = ensure_matches(s);
+    if(rc) return rc;
+    P.matches = s->matches; P.match_stride = (int)(s->matches_pitch / sizeof(float2));
+  }
+  P.cam = s->cam;
+  P.T_curr_ref = T_curr_ref;
+  P.T_ref_curr = pose_inverse(T_curr_ref);  // seed_matrix.cu:155
+  P.eta_inlier = s->eta_inlier; P.eta_outlier = s->eta_outlier; P.epsilon = s->epsilon;
+  P.depth_range = s->depth_range;
+  P.one_pix_angle = s->one_pix_angle;
+  P.tex_quant = s->tex_frac_bits > 0 ? (float)(1 << s->tex_frac_bits) : 0.0f;
+  P.trust_conv = s->trust_conv ? 1 : 0;
+  P.converged_now = s->counters + (s->frame_index & 1);
+  P.converged_next = s->counters + ((s->frame_index + 1) & 1);
+
+  if(s->timing) RMD_CUDA_TRY(cudaEventRecord(s->t0, s->stream));
+  if(s->variant == 0)
+  {
+    if(!s->maps) s->maps = new StagedMaps();
+    const int rc = s->maps->encode(P, s->patch);
+    if(rc) return rc;
+    RMD_CUDA_TRY(launch_depth_filter_staged(P, *s->maps, s->patch, s->stream));
+  }
+  else
+  {
+    RMD_CUDA_TRY(launch_depth_filter_direct(P, s->patch, s->stream));
+  }
+  if(s->timing)
+  {
+    RMD_CUDA_TRY(cudaEventRecord(s->t1, s->stream));
+    s->t_valid = true;
+  }
+  s->n_fused += 1;
+  s->n_total += 1;
+  s->trust_conv = true;
+  return 0;
+}
+
+// Stage a host frame (float or u8) into the next ring slot and make the
+// compute stream wait for it.  Returns the slot.
+int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *slot_out)
+{
+  const int slot = s->next_slot;
+  s->next_slot = (slot + 1) % kSlots;
+  const size_t row_bytes = elem_size * (size_t)s->width;
+  if(s->slot_used[slot])
+    RMD_CUDA_TRY(cudaEventSynchronize(s->copied[slot]));  // pinned buffer free again
+  memcpy(s->pinned[slot], host_img, row_bytes * s->height);
+  if(s->slot_used[slot])
+    RMD_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->consumed[slot], 0));
+  if(elem_size == sizeof(float))
+  {
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr[slot], s->curr_pitch, s->pinned[slot], row_bytes,
+                                   row_bytes, s->height, cudaMemcpyHostToDevice, s->copy_stream));
+  }
+  else
+  {
+    if(!s->curr_u8[slot])
+      RMD_CUDA_TRY(cudaMallocPitch(&s->curr_u8[slot], &s->curr_u8_pitch, (size_t)s->width, s->height));
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr_u8[slot], s->curr_u8_pitch, s->pinned[slot], row_bytes,
+                                   row_bytes, s->height, cudaMemcpyHostToDevice, s->copy_stream));
+  }
+  RMD_CUDA_TRY(cudaEventRecord(s->copied[slot], s->copy_stream));
+  RMD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->copied[slot], 0));
+  if(elem_size != sizeof(float))
+  {
+    RMD_CUDA_TRY(launch_u8_to_float(s->curr_u8[slot], (int)s->curr_u8_pitch, s->curr[slot],
+                                    (int)(s->curr_pitch / sizeof(float)), s->width, s->height,
+                                    s->stream));
+    s->n_total += 1;
+  }
+  s->slot_used[slot] = true;
+  *slot_out = slot;
+  return 0;
+}
+
+bool is_seed_field(int f) { return f >= RMD_FIELD_MU && f <= RMD_FIELD_B; }
+bool is_templ_field(int f) { return f == RMD_FIELD_SUM_TEMPL || f == RMD_FIELD_CONST_TEMPL_DENOM; }
+
+// Export a float field into a dense or pitched planar device image.
+int export_field(rmd_seeds *s, int field, float *dst, int dst_stride)
+{
+  if(is_seed_field(field))
+  {
+    RMD_CUDA_TRY(launch_export_plane(reinterpret_cast<const float*>(s->seed), s->seed_stride * 4, 4,
+                                     field - RMD_FIELD_MU, dst, dst_stride, s->width, s->height,
+                                     s->stream));
+  }
+  else if(is_templ_field(field))
+  {
+    RMD_CUDA_TRY(launch_export_plane(reinterpret_cast<const float*>(s->templ), s->templ_stride * 2, 2,
+                                     field - RMD_FIELD_SUM_TEMPL, dst, dst_stride, s->width,
+                                     s->height, s->stream));
+  }
+  else
+  {
+    return fail(RMD_ERR_INVALID_ARGUMENT, "export_field: not a float plane");
+  }
+  s->n_total += 1;
+  return 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+int rmd_abi_version(void) { return RMD_B200_ABI_VERSION; }
+
+const char *rmd_last_error_string(void) { return t_last_error.c_str(); }
+
+int rmd_device_count(int *count)
+{
+  RMD_REQUIRE(count, "rmd_device_count: null");
+  *count = 0;
+  RMD_CUDA_TRY(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float cy,
+                     int patch_side, int device, rmd_seeds_t **out)
+{
+  RMD_REQUIRE(out, "rmd_seeds_create: out is null");
+  *out = NULL;
+  RMD_REQUIRE(width > 0 && height > 0, "rmd_seeds_create: bad image size");
+  RMD_REQUIRE(patch_side == 5 || patch_side == 7, "rmd_seeds_create: patch_side must be 5 or 7");
+  RMD_REQUIRE(width > 2 * patch_side && height > 2 * patch_side,
+              "rmd_seeds_create: image smaller than the border ring");
+  if(device < 0) RMD_CUDA_TRY(cudaGetDevice(&device));
+  DeviceGuard guard(device);
+  int major = 0;
+  RMD_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if(major < 10)
+    return fail(RMD_ERR_UNSUPPORTED, "rmd_seeds_create: this library is built for sm_100a (B200) only");
+
+  rmd_seeds *s = new(std::nothrow) rmd_seeds();
+  if(!s) return fail((int)cudaErrorMemoryAllocation, "rmd_seeds_create: host allocation failed");
+  memset(s, 0, sizeof(*s));
+  s->device = device;
+  s->width = width; s->height = height; s->patch = patch_side;
+  s->cam.fx = fx; s->cam.fy = fy; s->cam.cx = cx; s->cam.cy = cy;
+  s->one_pix_angle = atan2f(1.0f, 2.0f * fx) * 2.0f;  // pinhole_camera.cuh:55-59
+  s->tex_frac_bits = 8;
+  s->variant = 1;
+  const int rc = seeds_alloc(s);
+  if(rc)
+  {
+    seeds_free(s);
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return 0;
+}
+
+int rmd_seeds_destroy(rmd_seeds_t *s)
+{
+  if(!s) return 0;
+  DeviceGuard guard(s->device);
+  seeds_free(s);
+  delete s;
+  return 0;
+}
+
+int rmd_seeds_set_stream(rmd_seeds_t *s, void *cuda_stream)
+{
+  RMD_REQUIRE(s, "rmd_seeds_set_stream: null handle");
+  DeviceGuard guard(s->device);
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+  return 0;
+}
+
+int rmd_seeds_get_stream(rmd_seeds_t *s, void **cuda_stream)
+{
+  RMD_REQUIRE(s && cuda_stream, "rmd_seeds_get_stream: null");
+  *cuda_stream = (void*)s->stream;
+  return 0;
+}
+
+int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
+{
+  RMD_REQUIRE(s, "rmd_seeds_set_option: null handle");
+  switch(option)
+  {
+  case RMD_OPT_RECORD_MATCHES: s->record_matches = (value != 0); return 0;
+  case RMD_OPT_KERNEL_VARIANT:
+    RMD_REQUIRE(value == 0 || value == 1, "RMD_OPT_KERNEL_VARIANT: 0 (staged) or 1 (direct)");
+    s->variant = value;
+    return 0;
+  case RMD_OPT_TEX_FRAC_BITS:
+    RMD_REQUIRE(value >= 0 && value <= 12, "RMD_OPT_TEX_FRAC_BITS: 0..12");
+    s->tex_frac_bits = value;
+    return 0;
+  default: return fail(RMD_ERR_INVALID_ARGUMENT, "rmd_seeds_set_option: unknown option");
+  }
+}
+
+int rmd_seeds_set_reference(rmd_seeds_t *s, const float *host_img, const float *T_curr_world,
+                            float min_depth, float max_depth)
+{
+  RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_set_reference: null argument");
+  DeviceGuard guard(s->device);
+  const size_t row = sizeof(float) * (size_t)s->width;
+  // pageable source: returns once the data is staged, buffer reusable
+  RMD_CUDA_TRY(cudaMemcpy2DAsync(s->ref, s->ref_pitch, host_img, row, row, s->height,
+                                 cudaMemcpyHostToDevice, s->stream));
+  return finish_set_reference(s, T_curr_world, min_depth, max_depth);
+}
+
+int rmd_seeds_set_reference_device(rmd_seeds_t *s, const float *dev_img, size_t pitch_bytes,
+                                   const float *T_curr_world, float min_depth, float max_depth)
+{
+  RMD_REQUIRE(s && dev_img && T_curr_world, "rmd_seeds_set_reference_device: null argument");
+  DeviceGuard guard(s->device);
+  const size_t row = sizeof(float) * (size_t)s->width;
+  RMD_REQUIRE(pitch_bytes >= row, "rmd_seeds_set_reference_device: pitch smaller than a row");
+  RMD_CUDA_TRY(cudaMemcpy2DAsync(s->ref, s->ref_pitch, dev_img, pitch_bytes, row, s->height,
+                                 cudaMemcpyDeviceToDevice, s->stream));
+  return finish_set_reference(s, T_curr_world, min_depth, max_depth);
+}
+
+int rmd_seeds_set_reference_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_curr_world,
+                               float min_depth, float max_depth)
+{
+  RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_set_reference_u8: null argument");
+  DeviceGuard guard(s->device);
+  if(!s->curr_u8[0])
+    RMD_CUDA_TRY(cudaMallocPitch(&s->curr_u8[0], &s->curr_u8_pitch, (size_t)s->width, s->height));
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+  RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr_u8[0], s->curr_u8_pitch, host_img, (size_t)s->width,
+                                 (size_t)s->width, s->height, cudaMemcpyHostToDevice, s->stream));
+  RMD_CUDA_TRY(launch_u8_to_float(s->curr_u8[0], (int)s->curr_u8_pitch, s->ref,
+                                  (int)(s->ref_pitch / sizeof(float)), s->width, s->height,
+                                  s->stream));
+  s->n_total += 1;
+  return finish_set_reference(s, T_curr_world, min_depth, max_depth);
+}
+
+int rmd_seeds_update(rmd_seeds_t *s, const float *host_img, const float *T_curr_world)
+{
+  RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_update: null argument");
+  if(!s->has_reference)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update: set_reference has not been called");
+  DeviceGuard guard(s->device);
+  int slot = 0;
+  const int rc = stage_host_frame(s, host_img, sizeof(float), &slot);
+  if(rc) return rc;
+  const int rc2 = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
+  if(rc2) return rc2;
+  RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
+  return 0;
+}
+
+int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_curr_world)
+{
+  RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_update_u8: null argument");
+  if(!s->has_reference)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_u8: set_reference has not been called");
+  DeviceGuard guard(s->device);
+  int slot = 0;
+  const int rc = stage_host_frame(s, host_img, sizeof(uint8_t), &slot);
+  if(rc) return rc;
+  const int rc2 = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
+  if(rc2) return rc2;
+  RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
+  return 0;
+}
+
+int rmd_seeds_update_device(rmd_seeds_t *s, const float *dev_img, size_t pitch_bytes,
+                            const float *T_curr_world)
+{
+  RMD_REQUIRE(s && dev_img && T_curr_world, "rmd_seeds_update_device: null argument");
+  RMD_REQUIRE(pitch_bytes >= sizeof(float) * (size_t)s->width && pitch_bytes % 16 == 0 &&
+              ((uintptr_t)dev_img % 16) == 0,
+              "rmd_seeds_update_device: image must be 16-byte aligned with a pitch multiple of 16");
+  if(!s->has_reference)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_device: set_reference has not been called");
+  DeviceGuard guard(s->device);
+  return enqueue_update(s, dev_img, pitch_bytes, T_curr_world);
+}
+
+int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_t frame_stride_bytes,
+                                  size_t pitch_bytes, int n_frames, const float *T_curr_world)
+{
+  RMD_REQUIRE(s && dev_frames && T_curr_world, "rmd_seeds_update_device_batch: null argument");
+  RMD_REQUIRE(n_frames >= 0, "rmd_seeds_update_device_batch: negative frame count");
+  RMD_REQUIRE(pitch_bytes >= sizeof(float) * (size_t)s->width && pitch_bytes % 16 == 0 &&
+              frame_stride_bytes % 16 == 0 && ((uintptr_t)dev_frames % 16) == 0,
+              "rmd_seeds_update_device_batch: frames must be 16-byte aligned with pitch/stride multiples of 16");
+  if(!s->has_reference)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_device_batch: set_reference has not been called");
+  DeviceGuard guard(s->device);
+  for(int i = 0; i < n_frames; ++i)
+  {
+    const float *frame = reinterpret_cast<const float*>(
+        reinterpret_cast<const char*>(dev_frames) + (size_t)i * frame_stride_bytes);
+    const int rc = enqueue_update(s, frame, pitch_bytes, T_curr_world + 12 * i);
+    if(rc) return rc;
+  }
+  return 0;
+}
+
+int rmd_seeds_sync(rmd_seeds_t *s)
+{
+  RMD_REQUIRE(s, "rmd_seeds_sync: null handle");
+  DeviceGuard guard(s->device);
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int rmd_seeds_download(rmd_seeds_t *s, int field, void *host_dst)
+{
+  RMD_REQUIRE(s && host_dst, "rmd_seeds_download: null argument");
+  DeviceGuard guard(s->device);
+  const size_t w = s->width, h = s->height;
+  if(is_seed_field(field) || is_templ_field(field))
+  {
+    int rc = ensure_dense_tmp(s);
+    if(rc) return rc;
+    rc = export_field(s, field, s->dense_tmp, s->width);
+    if(rc) return rc;
+    RMD_CUDA_TRY(cudaMemcpyAsync(host_dst, s->dense_tmp, sizeof(float) * w * h,
+                                 cudaMemcpyDeviceToHost, s->stream));
+  }
+  else if(field == RMD_FIELD_CONVERGENCE)
+  {
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(host_dst, sizeof(int) * w, s->conv, s->conv_pitch, sizeof(int) * w,
+                                   h, cudaMemcpyDeviceToHost, s->stream));
+  }
+  else if(field == RMD_FIELD_EPIPOLAR_MATCHES)
+  {
+    if(!s->matches)
+      return fail(RMD_ERR_NOT_INITIALISED,
+                  "rmd_seeds_download: matches are only kept with RMD_OPT_RECORD_MATCHES");
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(host_dst, sizeof(float2) * w, s->matches, s->matches_pitch,
+                                   sizeof(float2) * w, h, cudaMemcpyDeviceToHost, s->stream));
+  }
+  else if(field == RMD_FIELD_REF_IMG)
+  {
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(host_dst, sizeof(float) * w, s->ref, s->ref_pitch,
+                                   sizeof(float) * w, h, cudaMemcpyDeviceToHost, s->stream));
+  }
+  else
+  {
+    return fail(RMD_ERR_INVALID_ARGUMENT, "rmd_seeds_download: unknown field");
+  }
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
+{
+  RMD_REQUIRE(s && host_src, "rmd_seeds_upload_state: null argument");
+  DeviceGuard guard(s->device);
+  const size_t w = s->width, h = s->height;
+  if(is_seed_field(field))
+  {
+    const int rc = ensure_dense_tmp(s);
+    if(rc) return rc;
+    RMD_CUDA_TRY(cudaMemcpyAsync(s->dense_tmp, host_src, sizeof(float) * w * h,
+                                 cudaMemcpyHostToDevice, s->stream));
+    RMD_CUDA_TRY(launch_import_plane(s->dense_tmp, s->width, reinterpret_cast<float*>(s->seed),
+                                     s->seed_stride * 4, 4, field - RMD_FIELD_MU, s->width,
+                                     s->height, s->stream));
+    s->n_total += 1;
+  }
+  else if(field == RMD_FIELD_CONVERGENCE)
+  {
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(s->conv, s->conv_pitch, host_src, sizeof(int) * w, sizeof(int) * w,
+                                   h, cudaMemcpyHostToDevice, s->stream));
+  }
+  else
+  {
+    return fail(RMD_ERR_INVALID_ARGUMENT, "rmd_seeds_upload_state: field is not writable");
+  }
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->trust_conv = false;  // the map may no longer agree with the parameters
+  return 0;
+}
+
+int rmd_seeds_device_ptr(rmd_seeds_t *s, int field, void **dev_ptr, size_t *pitch_bytes)
+{
+  RMD_REQUIRE(s && dev_ptr && pitch_bytes, "rmd_seeds_device_ptr: null argument");
+  DeviceGuard guard(s->device);
+  if(field == RMD_FIELD_CONVERGENCE)
+  {
+    *dev_ptr = s->conv;
+    *pitch_bytes = s->conv_pitch;
+  }
+  else if(field == RMD_FIELD_REF_IMG)
+  {
+    *dev_ptr = s->ref;
+    *pitch_bytes = s->ref_pitch;
+  }
+  else if(is_seed_field(field) || is_templ_field(field))
+  {
+    const int slot = is_seed_field(field) ? field - RMD_FIELD_MU : 4 + field - RMD_FIELD_SUM_TEMPL;
+    if(!s->planar[slot])
+      RMD_CUDA_TRY(cudaMallocPitch(&s->planar[slot], &s->planar_pitch,
+                                   sizeof(float) * (size_t)s->width, s->height));
+    const int rc = export_field(s, field, s->planar[slot], (int)(s->planar_pitch / sizeof(float)));
+    if(rc) return rc;
+    *dev_ptr = s->planar[slot];
+    *pitch_bytes = s->planar_pitch;
+  }
+  else if(field == RMD_FIELD_EPIPOLAR_MATCHES)
+  {
+    if(!s->matches)
+      return fail(RMD_ERR_NOT_INITIALISED,
+                  "rmd_seeds_device_ptr: matches are only kept with RMD_OPT_RECORD_MATCHES");
+    *dev_ptr = s->matches;
+    *pitch_bytes = s->matches_pitch;
+  }
+  else
+  {
+    return fail(RMD_ERR_INVALID_ARGUMENT, "rmd_seeds_device_ptr: unknown field");
+  }
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int rmd_seeds_copy_field_to_device(rmd_seeds_t *s, int field, void *dev_dst, size_t dst_pitch_bytes)
+{
+  RMD_REQUIRE(s && dev_dst, "rmd_seeds_copy_field_to_device: null argument");
+  DeviceGuard guard(s->device);
+  const size_t w = s->width, h = s->height;
+  if(is_seed_field(field) || is_templ_field(field))
+  {
+    RMD_REQUIRE(dst_pitch_bytes >= sizeof(float) * w && dst_pitch_bytes % sizeof(float) == 0,
+                "rmd_seeds_copy_field_to_device: bad pitch");
+    return export_field(s, field, static_cast<float*>(dev_dst), (int)(dst_pitch_bytes / sizeof(float)));
+  }
+  if(field == RMD_FIELD_CONVERGENCE)
+  {
+    RMD_REQUIRE(dst_pitch_bytes >= sizeof(int) * w, "rmd_seeds_copy_field_to_device: bad pitch");
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(dev_dst, dst_pitch_bytes, s->conv, s->conv_pitch, sizeof(int) * w, h,
+                                   cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+  }
+  return fail(RMD_ERR_INVALID_ARGUMENT, "rmd_seeds_copy_field_to_device: unsupported field");
+}
+
+int rmd_seeds_converged_count(rmd_seeds_t *s, size_t *count)
+{
+  RMD_REQUIRE(s && count, "rmd_seeds_converged_count: null argument");
+  DeviceGuard guard(s->device);
+  unsigned int v = 0;
+  if(s->frame_index > 0)
+  {
+    RMD_CUDA_TRY(cudaMemcpyAsync(&v, s->counters + (s->frame_index & 1), sizeof(v),
+                                 cudaMemcpyDeviceToHost, s->stream));
+    RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  }
+  *count = v;
+  return 0;
+}
+
+int rmd_seeds_dist_from_ref(rmd_seeds_t *s, float *dist)
+{
+  RMD_REQUIRE(s && dist, "rmd_seeds_dist_from_ref: null argument");
+  *dist = s->dist_from_ref;
+  return 0;
+}
+
+int rmd_seeds_size(rmd_seeds_t *s, int *width, int *height, int *patch_side)
+{
+  RMD_REQUIRE(s, "rmd_seeds_size: null handle");
+  if(width) *width = s->width;
+  if(height) *height = s->height;
+  if(patch_side) *patch_side = s->patch;
+  return 0;
+}
+
+int rmd_seeds_launch_count(rmd_seeds_t *s, uint64_t *fused, uint64_t *total)
+{
+  RMD_REQUIRE(s, "rmd_seeds_launch_count: null handle");
+  if(fused) *fused = s->n_fused;
+  if(total) *total = s->n_total;
+  return 0;
+}
+
+int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on)
+{
+  RMD_REQUIRE(s, "rmd_seeds_enable_kernel_timing: null handle");
+  s->timing = (on != 0);
+  s->t_valid = false;
+  return 0;
+}
+
+int rmd_seeds_last_kernel_ms(rmd_seeds_t *s, float *ms)
+{
+  RMD_REQUIRE(s && ms, "rmd_seeds_last_kernel_ms: null argument");
+  if(!s->t_valid)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_last_kernel_ms: timing not enabled / no kernel yet");
+  DeviceGuard guard(s->device);
+  RMD_CUDA_TRY(cudaEventSynchronize(s->t1));
+  RMD_CUDA_TRY(cudaEventElapsedTime(ms, s->t0, s->t1));
+  return 0;
+}
+
+} // extern "C"
+
+// ============================================================== denoiser
+
+struct rmd_denoiser
+{
+  int device;
+  int width, height, stride;
+  cudaStream_t own_stream, stream;
+  float4 *state[2];
+  float2 *gmu;
+  float *dense_out;
+  float large_sigma_sq;
+  uint64_t n_total;
+};
+
+namespace
+{
+
+int denoiser_iterate(rmd_denoiser *d, float lambda, int iterations, int *final_buf)
+{
+  DenoiseStepParams sp;
+  sp.width = d->width; sp.height = d->height; sp.stride = d->stride;
+  sp.gmu = d->gmu;
+  const float L = sqrtf(8.0f);          // depthmap_denoiser.cu:130
+  sp.tau = 0.02f;                       // :131
+  sp.sigma = (1 / (L * L)) / sp.tau;    // :132
+  sp.theta = 0.5f;                      // :133
+  sp.lambda = lambda;
+  int cur = 0;
+  for(int i = 0; i < iterations; ++i)
+  {
+    sp.in = d->state[cur];
+    sp.out = d->state[cur ^ 1];
+    RMD_CUDA_TRY(launch_denoise_step(sp, d->stream));
+    cur ^= 1;
+  }
+  d->n_total += (uint64_t)(iterations > 0 ? iterations : 0);
+  *final_buf = cur;
+  return 0;
+}
+
+int denoiser_setup_common(rmd_denoiser *d, DenoiseSetupParams &P)
+{
+  P.width = d->width; P.height = d->height;
+  P.large_sigma_sq = d->large_sigma_sq;
+  P.gmu = d->gmu; P.state = d->state[0]; P.stride = d->stride;
+  return 0;
+}
+
+int denoiser_emit(rmd_denoiser *d, int buf, float *host_out, float *dev_out, size_t dev_pitch)
+{
+  const size_t w = d->width, h = d->height;
+  if(dev_out)
+  {
+    RMD_CUDA_TRY(launch_export_plane(reinterpret_cast<const float*>(d->state[buf]), d->stride * 4, 4, 0,
+                                     dev_out, (int)(dev_pitch / sizeof(float)), d->width, d->height,
+                                     d->stream));
+    d->n_total += 1;
+    return 0;
+  }
+  RMD_CUDA_TRY(launch_export_plane(reinterpret_cast<const float*>(d->state[buf]), d->stride * 4, 4, 0,
+                                   d->dense_out, d->width, d->width, d->height, d->stream));
+  d->n_total += 1;
+  RMD_CUDA_TRY(cudaMemcpyAsync(host_out, d->dense_out, sizeof(float) * w * h, cudaMemcpyDeviceToHost,
+                               d->stream));
+  RMD_CUDA_TRY(cudaStreamSynchronize(d->stream));  // u_.getDevData is blocking, :223
+  return 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+int rmd_denoiser_create(int width, int height, int device, rmd_denoiser_t **out)
+{
+  RMD_REQUIRE(out, "rmd_denoiser_create: out is null");
+  *out = NULL;
+  RMD_REQUIRE(width > 0 && height > 0, "rmd_denoiser_create: bad image size");
+  if(device < 0) RMD_CUDA_TRY(cudaGetDevice(&device));
+  DeviceGuard guard(device);
+  rmd_denoiser *d = new(std::nothrow) rmd_denoiser();
+  if(!d) return fail((int)cudaErrorMemoryAllocation, "rmd_denoiser_create: host allocation failed");
+  memset(d, 0, sizeof(*d));
+  d->device = device;
+  d->width = width; d->height = height;
+  d->stride = (int)round_up(width, 32);
+  d->large_sigma_sq = -1.0f;  // "not set" (the reference leaves it uninitialised)
+  cudaError_t err = cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking);
+  const size_t n = (size_t)d->stride * height;
+  if(err == cudaSuccess) err = cudaMalloc(&d->state[0], sizeof(float4) * n);
+  if(err == cudaSuccess) err = cudaMalloc(&d->state[1], sizeof(float4) * n);
+  if(err == cudaSuccess) err = cudaMalloc(&d->gmu, sizeof(float2) * n);
+  if(err == cudaSuccess) err = cudaMalloc(&d->dense_out, sizeof(float) * (size_t)width * height);
+  if(err != cudaSuccess)
+  {
+    rmd_denoiser_destroy(d);
+    return fail_cuda(err, "rmd_denoiser_create");
+  }
+  d->stream = d->own_stream;
+  *out = d;
+  return 0;
+}
+
+int rmd_denoiser_destroy(rmd_denoiser_t *d)
+{
+  if(!d) return 0;
+  DeviceGuard guard(d->device);
+  cudaDeviceSynchronize();
+  if(d->own_stream) cudaStreamDestroy(d->own_stream);
+  cudaFree(d->state[0]); cudaFree(d->state[1]); cudaFree(d->gmu); cudaFree(d->dense_out);
+  cudaGetLastError();
+  delete d;
+  return 0;
+}
+
+int rmd_denoiser_set_stream(rmd_denoiser_t *d, void *cuda_stream)
+{
+  RMD_REQUIRE(d, "rmd_denoiser_set_stream: null handle");
+  DeviceGuard guard(d->device);
+  RMD_CUDA_TRY(cudaStreamSynchronize(d->stream));
+  d->stream = cuda_stream ? (cudaStream_t)cuda_stream : d->own_stream;
+  return 0;
+}
+
+int rmd_denoiser_set_large_sigma_sq(rmd_denoiser_t *d, float depth_range)
+{
+  RMD_REQUIRE(d, "rmd_denoiser_set_large_sigma_sq: null handle");
+  d->large_sigma_sq = depth_range * depth_range / 72.0f;  // depthmap_denoiser.cu:228
+  return 0;
+}
+
+int rmd_denoiser_run(rmd_denoiser_t *d, const float *mu, size_t mu_pitch, const float *sigma_sq,
+                     size_t sigma_sq_pitch, const float *a, size_t a_pitch, const float *b,
+                     size_t b_pitch, float *host_denoised, float lambda, int iterations)
+{
+  RMD_REQUIRE(d && mu && sigma_sq && a && b && host_denoised, "rmd_denoiser_run: null argument");
+  RMD_REQUIRE(iterations >= 0, "rmd_denoiser_run: negative iteration count");
+  if(d->large_sigma_sq < 0.0f)
+    return fail(RMD_ERR_NOT_INITIALISED,
+                "rmd_denoiser_run: set_large_sigma_sq must be called before this function");
+  DeviceGuard guard(d->device);
+  // Inputs may have been produced on another stream (the seed matrix' own):
+  // the reference runs everything on the legacy default stream, which orders
+  // it implicitly; here the caller's last call on the seeds handle
+  // (device_ptr) has already synchronised that stream.
+  DenoiseSetupParams P;
+  memset(&P, 0, sizeof(P));
+  denoiser_setup_common(d, P);
+  P.mu = mu; P.mu_stride = (int)(mu_pitch / sizeof(float));
+  P.sigma_sq = sigma_sq; P.sigma_sq_stride = (int)(sigma_sq_pitch / sizeof(float));
+  P.a = a; P.a_stride = (int)(a_pitch / sizeof(float));
+  P.b = b; P.b_stride = (int)(b_pitch / sizeof(float));
+  RMD_CUDA_TRY(launch_denoise_setup(P, false, d->stream));
+  d->n_total += 1;
+  int buf = 0;
+  const int rc = denoiser_iterate(d, lambda, iterations, &buf);
+  if(rc) return rc;
+  return denoiser_emit(d, buf, host_denoised, NULL, 0);
+}
+
+static int run_seeds_common(rmd_denoiser_t *d, rmd_seeds_t *s, float lambda, int iterations, int *buf)
+{
+  if(d->large_sigma_sq < 0.0f)
+    return fail(RMD_ERR_NOT_INITIALISED,
+                "rmd_denoiser_run_seeds: set_large_sigma_sq must be called before this function");
+  RMD_REQUIRE(s->width == d->width && s->height == d->height && s->device == d->device,
+              "rmd_denoiser_run_seeds: seed matrix and denoiser differ in size or device");
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));  // the seeds must be final
+  DenoiseSetupParams P;
+  memset(&P, 0, sizeof(P));
+  denoiser_setup_common(d, P);
+  P.seed = s->seed; P.seed_stride = s->seed_stride;
+  RMD_CUDA_TRY(launch_denoise_setup(P, true, d->stream));
+  d->n_total += 1;
+  return denoiser_iterate(d, lambda, iterations, buf);
+}
+
+int rmd_denoiser_run_seeds(rmd_denoiser_t *d, rmd_seeds_t *s, float *host_denoised, float lambda,
+                           int iterations)
+{
+  RMD_REQUIRE(d && s && host_denoised, "rmd_denoiser_run_seeds: null argument");
+  RMD_REQUIRE(iterations >= 0, "rmd_denoiser_run_seeds: negative iteration count");
+  DeviceGuard guard(d->device);
+  int buf = 0;
+  const int rc = run_seeds_common(d, s, lambda, iterations, &buf);
+  if(rc) return rc;
+  return denoiser_emit(d, buf, host_denoised, NULL, 0);
+}
+
+int rmd_denoiser_run_seeds_to_device(rmd_denoiser_t *d, rmd_seeds_t *s, float *dev_out,
+                                     size_t out_pitch_bytes, float lambda, int iterations)
+{
+  RMD_REQUIRE(d && s && dev_out, "rmd_denoiser_run_seeds_to_device: null argument");
+  RMD_REQUIRE(iterations >= 0, "rmd_denoiser_run_seeds_to_device: negative iteration count");
+  RMD_REQUIRE(out_pitch_bytes >= sizeof(float) * (size_t)d->width && out_pitch_bytes % sizeof(float) == 0,
+              "rmd_denoiser_run_seeds_to_device: bad pitch");
+  DeviceGuard guard(d->device);
+  int buf = 0;
+  const int rc = run_seeds_common(d, s, lambda, iterations, &buf);
+  if(rc) return rc;
+  return denoiser_emit(d, buf, NULL, dev_out, out_pitch_bytes);
+}
+
+int rmd_denoiser_sync(rmd_denoiser_t *d)
+{
+  RMD_REQUIRE(d, "rmd_denoiser_sync: null handle");
+  DeviceGuard guard(d->device);
+  RMD_CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int rmd_denoiser_launch_count(rmd_denoiser_t *d, uint64_t *total)
+{
+  RMD_REQUIRE(d && total, "rmd_denoiser_launch_count: null argument");
+  *total = d->n_total;
+  return 0;
+}
+
+} // extern "C"
+
+// ============================================================ reductions
+
+namespace
+{
+
+struct ReduceContext
+{
+  ReduceScratch scratch;
+  bool ready;
+};
+
+std::mutex g_reduce_mutex;
+ReduceContext g_reduce_ctx[64];
+
+// Scratch of the calling thread's current device (allocated on first use).
+int reduce_scratch(ReduceScratch **out)
+{
+  int device = 0;
+  RMD_CUDA_TRY(cudaGetDevice(&device));
+  RMD_REQUIRE(device >= 0 && device < 64, "reduce: device index out of range");
+  ReduceContext &ctx = g_reduce_ctx[device];
+  if(!ctx.ready)
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    ctx.scratch.max_blocks = sms * 4;
+    RMD_CUDA_TRY(cudaMalloc(&ctx.scratch.partials, sizeof(double) * 2 * (size_t)ctx.scratch.max_blocks));
+    RMD_CUDA_TRY(cudaMalloc(&ctx.scratch.ticket, sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMemset(ctx.scratch.ticket, 0, sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMalloc(&ctx.scratch.result, 16));
+    ctx.ready = true;
+  }
+  *out = &ctx.scratch;
+  return 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+// The reference's reducers run on the legacy default stream and block on a
+// 4-byte cudaMemcpy (src/reduction.cu:108,163); same here, so they order
+// after whatever the caller enqueued on blocking streams.
+int rmd_reduce_sum_f32(const float *dev_img, size_t stride, size_t width, size_t height, float *out)
+{
+  RMD_REQUIRE(dev_img && out, "rmd_reduce_sum_f32: null argument");
+  std::lock_guard<std::mutex> lock(g_reduce_mutex);
+  ReduceScratch *sc = NULL;
+  const int rc = reduce_scratch(&sc);
+  if(rc) return rc;
+  RMD_CUDA_TRY(launch_sum_f32(dev_img, stride, width, height, *sc, 0));
+  double r[2];
+  RMD_CUDA_TRY(cudaMemcpy(r, sc->result, sizeof(r), cudaMemcpyDeviceToHost));
+  *out = (float)r[0];
+  return 0;
+}
+
+int rmd_reduce_sum_i32(const int32_t *dev_img, size_t stride, size_t width, size_t height,
+                       int32_t *out)
+{
+  RMD_REQUIRE(dev_img && out, "rmd_reduce_sum_i32: null argument");
+  std::lock_guard<std::mutex> lock(g_reduce_mutex);
+  ReduceScratch *sc = NULL;
+  const int rc = reduce_scratch(&sc);
+  if(rc) return rc;
+  RMD_CUDA_TRY(launch_sum_i32(dev_img, stride, width, height, *sc, 0));
+  long long r[2];
+  RMD_CUDA_TRY(cudaMemcpy(r, sc->result, sizeof(r), cudaMemcpyDeviceToHost));
+  *out = (int32_t)r[0];  // wraps like the reference's int accumulation
+  return 0;
+}
+
+int rmd_reduce_count_eq_i32(const int32_t *dev_img, size_t stride, size_t width, size_t height,
+                            int32_t value, size_t *out)
+{
+  RMD_REQUIRE(dev_img && out, "rmd_reduce_count_eq_i32: null argument");
+  std::lock_guard<std::mutex> lock(g_reduce_mutex);
+  ReduceScratch *sc = NULL;
+  const int rc = reduce_scratch(&sc);
+  if(rc) return rc;
+  RMD_CUDA_TRY(launch_count_eq_i32(dev_img, stride, width, height, value, *sc, 0));
+  long long r[2];
+  RMD_CUDA_TRY(cudaMemcpy(r, sc->result, sizeof(r), cudaMemcpyDeviceToHost));
+  *out = (size_t)r[0];
+  return 0;
+}
+
+int rmd_reduce_min_max_f32(const float *dev_img, size_t stride, size_t width, size_t height,
+                           float *out_min, float *out_max)
+{
+  RMD_REQUIRE(dev_img && out_min && out_max, "rmd_reduce_min_max_f32: null argument");
+  std::lock_guard<std::mutex> lock(g_reduce_mutex);
+  ReduceScratch *sc = NULL;
+  const int rc = reduce_scratch(&sc);
+  if(rc) return rc;
+  RMD_CUDA_TRY(launch_min_max_f32(dev_img, stride, width, height, *sc, 0));
+  double r[2];
+  RMD_CUDA_TRY(cudaMemcpy(r, sc->result, sizeof(r), cudaMemcpyDeviceToHost));
+  *out_min = (float)r[0];
+  *out_max = (float)r[1];
+  return 0;
+}
+
+// ========================================================== device image
+
+int rmd_image_alloc(size_t width, size_t height, size_t elem_size, void **dev_ptr, size_t *pitch_bytes)
+{
+  RMD_REQUIRE(dev_ptr && pitch_bytes && width && height && elem_size, "rmd_image_alloc: bad argument");
+  RMD_CUDA_TRY(cudaMallocPitch(dev_ptr, pitch_bytes, width * elem_size, height));
+  return 0;
+}
+
+int rmd_image_free(void *dev_ptr)
+{
+  RMD_CUDA_TRY(cudaFree(dev_ptr));
+  return 0;
+}
+
+int rmd_image_upload(void *dev_ptr, size_t pitch_bytes, const void *host_src, size_t width,
+                     size_t height, size_t elem_size)
+{
+  RMD_REQUIRE(dev_ptr && host_src, "rmd_image_upload: null argument");
+  RMD_CUDA_TRY(cudaMemcpy2D(dev_ptr, pitch_bytes, host_src, width * elem_size, width * elem_size,
+                            height, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int rmd_image_download(const void *dev_ptr, size_t pitch_bytes, void *host_dst, size_t width,
+                       size_t height, size_t elem_size)
+{
+  RMD_REQUIRE(dev_ptr && host_dst, "rmd_image_download: null argument");
+  RMD_CUDA_TRY(cudaMemcpy2D(host_dst, width * elem_size, dev_ptr, pitch_bytes, width * elem_size,
+                            height, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int rmd_image_zero(void *dev_ptr, size_t pitch_bytes, size_t width, size_t height, size_t elem_size)
+{
+  RMD_REQUIRE(dev_ptr, "rmd_image_zero: null argument");
+  RMD_CUDA_TRY(cudaMemset2D(dev_ptr, pitch_bytes, 0, width * elem_size, height));
+  return 0;
+}
+
+int rmd_image_copy(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width,
+                   size_t height, size_t elem_size)
+{
+  RMD_REQUIRE(dst && src, "rmd_image_copy: null argument");
+  RMD_CUDA_TRY(cudaMemcpy2D(dst, dst_pitch, src, src_pitch, width * elem_size, height,
+                            cudaMemcpyDeviceToDevice));
+  return 0;
+}
+
+} // extern "C"

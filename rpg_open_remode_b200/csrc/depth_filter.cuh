@@ -1,0 +1,42 @@
+// depth_filter.cuh -- launch interface of the seed-matrix kernels.
+#pragma once
+
+#include "rmd_common.cuh"
+
+namespace rmdb
+{
+
+struct InitParams
+{
+  int width, height;
+  const float *ref;
+  int ref_stride;
+  float4 *seed;
+  int seed_stride;
+  float2 *templ;
+  int templ_stride;
+  int *conv;
+  int conv_stride;
+  float avg_depth, sigma_sq_max;
+};
+
+cudaError_t launch_seed_init(const InitParams &P, int patch_side, cudaStream_t stream);
+
+// One thread per pixel, global loads.
+cudaError_t launch_depth_filter_direct(const FilterParams &P, int patch_side, cudaStream_t stream);
+
+// TMA-staged shared-memory variant (depth_filter_staged.cu).  `maps` is the
+// host-side descriptor set built by StagedMaps::encode for this frame.
+struct StagedMaps;
+cudaError_t launch_depth_filter_staged(const FilterParams &P, const StagedMaps &maps,
+                                       int patch_side, cudaStream_t stream);
+
+cudaError_t launch_u8_to_float(const uint8_t *src, int src_stride, float *dst, int dst_stride,
+                               int width, int height, cudaStream_t stream);
+cudaError_t launch_export_plane(const float *src, int src_stride_floats, int comps, int comp,
+                                float *dst, int dst_stride, int width, int height,
+                                cudaStream_t stream);
+cudaError_t launch_import_plane(const float *src, int src_stride, float *dst, int dst_stride_floats,
+                                int comps, int comp, int width, int height, cudaStream_t stream);
+
+} // namespace rmdb
