@@ -125,8 +125,9 @@ class ClockSampler:
 def load_sequence(args, rank):
     """Renders the rank's synthetic sequence on the host (float32 frames,
     uint8-quantised like the reference's MONO8 input, src/depthmap.cpp:105)."""
-    from rpg_open_remode_b200 import synth
-    seq = synth.SyntheticSequence(args.width, args.height, seed=0x5EED0002 + 16 * rank)
+    from rpg_open_remode_b200 import multi_gpu, synth
+    # one keyframe per rank: rank r owns keyframe r (multi_gpu.shard_keyframes(world, r, world) == [r])
+    seq = synth.SyntheticSequence(args.width, args.height, seed=multi_gpu.keyframe_seed(rank))
     n = args.frames
     frames = np.empty((n, args.height, args.width), np.float32)
     poses = np.empty((n, 12), np.float32)   # T_curr_world (world -> camera)
@@ -172,6 +173,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import rpg_open_remode_b200 as rmd
+    from rpg_open_remode_b200 import multi_gpu
 
     if not torch.cuda.is_available() or rmd.device_count() < 1:
         raise RuntimeError("bench.py: no CUDA device -- the product has no CPU path")
@@ -184,7 +186,13 @@ def run_ours(args, rank, world, local_rank):
     seeds = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera), patch_side=args.patch, device=local_rank)
     variant = args.variant or os.environ.get("RMD_BENCH_VARIANT", "staged")
     seeds.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED if variant == "staged" else rmd.VARIANT_DIRECT)
-    stream = torch.cuda.current_stream(dev)
+    # A dedicated (non-default) torch stream is made current and handed to the
+    # handle, so the fused kernels, torch's NCCL calls and the CUDA events that
+    # time them are all on the same stream (torch's default stream is handle 0,
+    # which the C-ABI reads as "use the handle's own stream").
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     seeds.setStream(stream.cuda_stream)
 
     # frames resident in HBM for `value`; pinned host frames for `e2e`
@@ -193,16 +201,12 @@ def run_ours(args, rank, world, local_rank):
     frame_bytes = W * H * 4
     depth_out = torch.empty((H, W), dtype=torch.float32, device=dev)
     conv_out = torch.empty((H, W), dtype=torch.int32, device=dev)
-    gather_depth = [torch.empty_like(depth_out) for _ in range(world)] if (world > 1 and rank == 0) else None
-    gather_conv = [torch.empty_like(conv_out) for _ in range(world)] if (world > 1 and rank == 0) else None
 
     def final_gather():
         # the only collective on the path: final depth + convergence maps to rank 0 (NCCL)
         seeds.copyFieldToDevice(rmd.FIELD_MU, depth_out.data_ptr(), W * 4)
         seeds.copyFieldToDevice(rmd.FIELD_CONVERGENCE, conv_out.data_ptr(), W * 4)
-        if world > 1:
-            dist.gather(depth_out, gather_depth, dst=0)
-            dist.gather(conv_out, gather_conv, dst=0)
+        return multi_gpu.gather_maps(depth_out, conv_out, dst=0)
 
     def step_resident():
         seeds.setReferenceImageDevice(dev_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)
@@ -225,11 +229,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     def max_over_ranks(v):
-        if world > 1:
-            t = torch.tensor([v], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return v
+        return multi_gpu.max_over_ranks(v, dev)
 
     # ---------------- device-resident timing (value)
     for _ in range(args.warmup):

@@ -1,22 +1,493 @@
-// depth_filter_staged.cu -- TMA-staged variant of the fused depth filter.
-// (placeholder until the staged kernel lands: reports "not supported" so the
-// caller can never silently fall back)
+// depth_filter_staged.cu -- fused depth filter, staged variant for sm_100a.
+//
+// One CTA = 32x8 pixels of the reference view (one warp per row).  Per frame:
+//   0. classify every seed (convergence check, src/seed_check.cu:29-67);
+//      CTAs without a seed left to update stop here after 4 B/pixel;
+//   1. every active seed projects its depth interval into the current frame
+//      (src/epipolar_match.cu:60-75) and the CTA reduces the bounding box of
+//      all its search segments;
+//   2. one thread issues TMA loads (cp.async.bulk.tensor.2d, mbarrier
+//      complete_tx) of the reference tile (+halo) and of that strip of the
+//      current frame into shared memory;
+//   3. each warp flattens the (seed, 8-candidate chunk) pairs of its 32 seeds
+//      into a chunk-major work list and hands items to lanes round-robin, so
+//      lanes stay busy whatever the mix of search lengths; the NCC of a
+//      candidate is evaluated by the same code as in the direct variant
+//      (depth_filter_math.cuh) on taps read from the shared-memory strip
+//      (from global memory for the rare block outside it); per-seed arg-max
+//      is combined with a shared-memory 64-bit atomicMax on (ncc, -index),
+//      which reproduces the reference's "first maximum wins" order
+//      (epipolar_match.cu:125-129);
+//   4. the owner thread triangulates the best match and updates its seed
+//      (src/seed_update.cu:40-121) in registers and writes it back once.
+// Results are bit-identical to the direct variant.
+#include <cudaTypedefs.h>
+
+#include <limits.h>
+
 #include "depth_filter.cuh"
+#include "depth_filter_math.cuh"
 #include "staged_maps.cuh"
 
 namespace rmdb
 {
 
-StagedMaps::StagedMaps() : patch(0), ref_ptr(NULL), curr_ptr(NULL), ref_stride(0), curr_stride(0), width(0), height(0) {}
+using namespace staged;
 
-int StagedMaps::encode(const FilterParams &, int)
+namespace
 {
-  return fail(RMD_ERR_UNSUPPORTED, "staged depth-filter kernel is not built into this library");
+
+struct SearchRec  // one active seed's search, 32 bytes
+{
+  float mean_x, mean_y, dir_x, dir_y, half_len, sum_templ, denom;
+  int n;
+};
+
+template<int PS>
+struct __align__(128) StagedSmem
+{
+  float strip[STRIP_FLOATS];
+  float ref[REF_BOX_W * ref_box_h(PS)];
+  SearchRec rec[NTHREADS];
+  unsigned long long best[NTHREADS];
+  unsigned int level_mask[TILE_H][MAX_CHUNKS + 2];
+  int level_cum[TILE_H][MAX_CHUNKS + 2];
+  int bbox[4];       // xmin, ymin, xmax, ymax over all segments of the CTA
+  int strip_ox, strip_oy, strip_w, strip_rows;
+  unsigned long long mbar;
+};
+
+// ------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ unsigned int smem_addr(const void *p)
+{
+  return (unsigned int)__cvta_generic_to_shared(p);
 }
 
-cudaError_t launch_depth_filter_staged(const FilterParams &, const StagedMaps &, int, cudaStream_t)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count)
 {
-  return cudaErrorNotSupported;
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned int parity)
+{
+  unsigned int ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0u;
+}
+
+// Bounded wait: a TMA that never completes (bad descriptor) must fail the
+// launch, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+  for(unsigned int it = 0; !mbar_try_wait(bar, parity); ++it)
+    if(it > (1u << 22)) __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                            unsigned long long *bar)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];"
+      :: "r"(smem_addr(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1),
+         "r"(smem_addr(bar))
+      : "memory");
+}
+
+// float -> unsigned with the same ordering (for atomicMax on NCC scores)
+__device__ __forceinline__ unsigned int orderable(float f)
+{
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Texel block of a candidate inside the shared-memory strip.
+struct StripTaps
+{
+  const float *origin;
+  int stride;
+  __device__ __forceinline__ StripTaps(const float *strip, int strip_w, int ox, int oy, const TapFrame &t)
+    : origin(strip + (t.j0 - oy) * strip_w + (t.i0 - ox)), stride(strip_w) {}
+  __device__ __forceinline__ float at(const int j, const int i) const { return origin[j * stride + i]; }
+};
+
+__device__ __forceinline__ int to_int_clamped(float v)
+{
+  return (int)fminf(fmaxf(v, -1.0e6f), 1.0e6f);  // NaN -> -1e6 (fmaxf drops NaN)
+}
+
+} // namespace
+
+template<int PS>
+__global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_staged_kernel(
+    const __grid_constant__ FilterParams P, const __grid_constant__ StagedTensorMaps M)
+{
+  extern __shared__ unsigned char smem_raw[];
+  StagedSmem<PS> &S = *reinterpret_cast<StagedSmem<PS>*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int tid = warp * TILE_W + lane;
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+  const int x = x0 + lane, y = y0 + warp;
+
+  if(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+    *P.converged_next = 0u;
+
+  // ---- 0. classification
+  bool active = false, converged = false;
+  int prev = RMD_BORDER, state = RMD_BORDER;
+  int *conv_ptr = nullptr;
+  float4 *seed_ptr = nullptr;
+  float4 seed = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool inside = (x < P.width) && (y < P.height);
+  if(inside)
+  {
+    conv_ptr = P.conv + (size_t)y * P.conv_stride + x;
+    prev = *conv_ptr;
+    if(P.trust_conv && (prev == RMD_BORDER || prev == RMD_CONVERGED || prev == RMD_DIVERGED))
+    {
+      state = prev;
+    }
+    else if((x > P.width - PS - 1) || (y > P.height - PS - 1) || (x < PS) || (y < PS))
+    {
+      state = RMD_BORDER;
+    }
+    else
+    {
+      seed_ptr = P.seed + (size_t)y * P.seed_stride + x;
+      seed = *seed_ptr;
+      state = classify_seed(P, seed);
+      active = (state == RMD_UPDATE);
+    }
+    converged = (state == RMD_CONVERGED);
+    if(!active && state != prev)
+      *conv_ptr = state;
+  }
+  {
+    const unsigned int ballot = __ballot_sync(0xffffffffu, converged);
+    if(lane == 0 && ballot)
+      atomicAdd(P.converged_now, (unsigned int)__popc(ballot));
+  }
+  if(tid == 0)
+  {
+    S.bbox[0] = INT_MAX; S.bbox[1] = INT_MAX; S.bbox[2] = INT_MIN; S.bbox[3] = INT_MIN;
+    mbar_init(&S.mbar, 1);
+  }
+  const int n_active = __syncthreads_count(active);
+  if(n_active == 0)
+    return;
+
+  // ---- 1. search segments, candidate counts, bounding box
+  EpiSegment seg;
+  seg.mean = make_float2(0.f, 0.f); seg.dir = make_float2(0.f, 0.f); seg.half_len = 0.f;
+  int n_cand = 0;
+  int bx_lo = INT_MAX, by_lo = INT_MAX, bx_hi = INT_MIN, by_hi = INT_MIN;
+  if(active)
+  {
+    seg = epipolar_segment(P, x, y, seed.x, seed.y);
+    for(float l = -seg.half_len; l <= seg.half_len; l += RMD_EPIPOLAR_STEP)
+      ++n_cand;
+    const float ex0 = seg.mean.x - seg.half_len * seg.dir.x, ex1 = seg.mean.x + seg.half_len * seg.dir.x;
+    const float ey0 = seg.mean.y - seg.half_len * seg.dir.y, ey1 = seg.mean.y + seg.half_len * seg.dir.y;
+    int xl = to_int_clamped(floorf(fminf(ex0, ex1))) - (PS / 2 + 1);
+    int xh = to_int_clamped(floorf(fmaxf(ex0, ex1))) + (PS / 2 + 3);
+    int yl = to_int_clamped(floorf(fminf(ey0, ey1))) - (PS / 2 + 1);
+    int yh = to_int_clamped(floorf(fmaxf(ey0, ey1))) + (PS / 2 + 3);
+    // only the part where candidates are accepted matters (epipolar_match.cu:91-97)
+    xl = max(xl, PS - PS / 2 - 1); yl = max(yl, PS - PS / 2 - 1);
+    xh = min(xh, P.width - 1);     yh = min(yh, P.height - 1);
+    if(n_cand > 0 && xl <= xh && yl <= yh)
+    {
+      bx_lo = xl; bx_hi = xh; by_lo = yl; by_hi = yh;
+    }
+    const float2 stats = __ldg(P.templ + (size_t)y * P.templ_stride + x);
+    SearchRec r;
+    r.mean_x = seg.mean.x; r.mean_y = seg.mean.y; r.dir_x = seg.dir.x; r.dir_y = seg.dir.y;
+    r.half_len = seg.half_len; r.sum_templ = stats.x; r.denom = stats.y; r.n = n_cand;
+    S.rec[tid] = r;
+  }
+  const unsigned long long kNoMatch = ((unsigned long long)orderable(-1.0f)) << 32;
+  S.best[tid] = kNoMatch;
+  bx_lo = __reduce_min_sync(0xffffffffu, bx_lo); by_lo = __reduce_min_sync(0xffffffffu, by_lo);
+  bx_hi = __reduce_max_sync(0xffffffffu, bx_hi); by_hi = __reduce_max_sync(0xffffffffu, by_hi);
+  if(lane == 0 && bx_lo <= bx_hi)
+  {
+    atomicMin(&S.bbox[0], bx_lo); atomicMin(&S.bbox[1], by_lo);
+    atomicMax(&S.bbox[2], bx_hi); atomicMax(&S.bbox[3], by_hi);
+  }
+  __syncthreads();
+
+  // ---- 2. TMA: reference tile and current-image strip -> shared memory
+  if(tid == 0)
+  {
+    const int xmin = S.bbox[0], ymin = S.bbox[1], xmax = S.bbox[2], ymax = S.bbox[3];
+    int ox = 0, oy = 0, sw = 0, rows = 0, wi = 0;
+    if(xmin <= xmax && ymin <= ymax)
+    {
+      const int bw = xmax - xmin + 1, bh = ymax - ymin + 1;
+      wi = NUM_WIDTHS - 1;
+#pragma unroll
+      for(int i = NUM_WIDTHS - 1; i >= 0; --i)
+        if(strip_width(i) >= bw) wi = i;
+      sw = strip_width(wi);
+      const int max_rows = (STRIP_FLOATS / sw) / STRIP_BOX_ROWS * STRIP_BOX_ROWS;
+      const int want_rows = (bh + STRIP_BOX_ROWS - 1) / STRIP_BOX_ROWS * STRIP_BOX_ROWS;
+      rows = min(want_rows, max_rows);
+      ox = (bw <= sw) ? xmin : xmin + (bw - sw) / 2;
+      oy = (want_rows <= max_rows) ? ymin : ymin + (bh - rows) / 2;
+    }
+    S.strip_ox = ox; S.strip_oy = oy; S.strip_w = sw; S.strip_rows = rows;
+    const unsigned int ref_bytes = REF_BOX_W * ref_box_h(PS) * (unsigned int)sizeof(float);
+    mbar_expect_tx(&S.mbar, ref_bytes + (unsigned int)(rows * sw) * (unsigned int)sizeof(float));
+    tma_load_2d(S.ref, &M.ref, x0 - PS / 2, y0 - PS / 2, &S.mbar);
+    const CUtensorMap *cm = &M.curr[wi];
+    for(int r = 0; r < rows; r += STRIP_BOX_ROWS)
+      tma_load_2d(S.strip + r * sw, cm, ox, oy + r, &S.mbar);
+  }
+  __syncthreads();
+  const int strip_ox = S.strip_ox, strip_oy = S.strip_oy, strip_w = S.strip_w, strip_rows = S.strip_rows;
+  mbar_wait(&S.mbar, 0);
+
+  // ---- 3. balanced NCC search: chunk-major work list per warp
+  {
+    const int m = (n_cand + CHUNK - 1) / CHUNK;  // chunks of my seed (0 if inactive)
+    unsigned int my_mask = 0u;
+#pragma unroll
+    for(int c = 0; c < MAX_CHUNKS; ++c)
+    {
+      const unsigned int mk = __ballot_sync(0xffffffffu, m > c);
+      if(lane == c) my_mask = mk;
+    }
+    const int cnt = __popc(my_mask);
+    int inc = cnt;
+#pragma unroll
+    for(int off = 1; off < 32; off <<= 1)
+    {
+      const int v = __shfl_up_sync(0xffffffffu, inc, off);
+      if(lane >= off) inc += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if(lane < MAX_CHUNKS + 2)
+    {
+      S.level_mask[warp][lane] = my_mask;
+      S.level_cum[warp][lane] = inc - cnt;  // items before level `lane`
+    }
+    __syncwarp();
+
+    for(int q = lane; q < total; q += 32)
+    {
+      int c = 0;
+      while(c + 1 < MAX_CHUNKS && S.level_cum[warp][c + 1] <= q) ++c;
+      const int rank = q - S.level_cum[warp][c];
+      const int src = __fns(S.level_mask[warp][c], 0, rank + 1);  // lane owning the seed
+
+      const SearchRec R = S.rec[warp * TILE_W + src];
+      float templ[PS * PS];
+#pragma unroll
+      for(int j = 0; j < PS; ++j)
+#pragma unroll
+        for(int i = 0; i < PS; ++i)
+          templ[j * PS + i] = S.ref[(warp + j) * REF_BOX_W + src + i];
+
+      // l of the chunk's first candidate: the same float accumulation as the
+      // reference's loop (epipolar_match.cu:88), so positions are bit-identical
+      float l = -R.half_len;
+      const int first = c * CHUNK;
+      for(int k = 0; k < first; ++k) l += RMD_EPIPOLAR_STEP;
+
+      float best_ncc = -1.0f;
+      int best_idx = 0;
+#pragma unroll 1
+      for(int i = 0; i < CHUNK; ++i, l += RMD_EPIPOLAR_STEP)
+      {
+        if(!(l <= R.half_len)) break;
+        const float2 px = make_float2(R.mean_x + l * R.dir_x, R.mean_y + l * R.dir_y);
+        if(candidate_rejected<PS>(px, P.width, P.height))
+          continue;
+        const TapFrame frame = tap_frame<PS>(px, P.tex_quant);
+        const bool in_strip = (frame.i0 >= strip_ox) && (frame.i0 + PS < strip_ox + strip_w) &&
+                              (frame.j0 >= strip_oy) && (frame.j0 + PS < strip_oy + strip_rows);
+        float ncc;
+        if(in_strip)
+        {
+          const StripTaps taps(S.strip, strip_w, strip_ox, strip_oy, frame);
+          ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+        }
+        else
+        {
+          const GlobalTaps taps(P.curr, P.curr_stride, frame);
+          ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+        }
+        if(ncc > best_ncc)
+        {
+          best_ncc = ncc;
+          best_idx = first + i;
+        }
+      }
+      if(best_ncc > -1.0f)
+      {
+        const unsigned long long key =
+            (((unsigned long long)orderable(best_ncc)) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)best_idx);
+        atomicMax(&S.best[warp * TILE_W + src], key);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- 4. triangulation + Bayesian update by the owner of the seed
+  if(active)
+  {
+    const unsigned long long key = S.best[tid];
+    if(key == kNoMatch || !(n_cand > 0))
+    {
+      state = RMD_NO_MATCH;
+    }
+    else
+    {
+      const unsigned int hi = (unsigned int)(key >> 32);
+      const float best_ncc = __uint_as_float((hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi);
+      if(best_ncc < RMD_NCC_ACCEPT)
+      {
+        state = RMD_NO_MATCH;
+      }
+      else
+      {
+        const int best_idx = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull));
+        float l = -seg.half_len;
+        for(int k = 0; k < best_idx; ++k) l += RMD_EPIPOLAR_STEP;
+        const float2 best_px = make_float2(seg.mean.x + l * seg.dir.x, seg.mean.y + l * seg.dir.y);
+        if(P.matches)
+          P.matches[(size_t)y * P.match_stride + x] = best_px;
+        if(bayes_update(P, x, y, best_px, seed))
+          *seed_ptr = seed;
+      }
+    }
+    if(state == RMD_NO_MATCH)
+    {
+      seed.w += 1.0f;  // seed_update.cu:113-117
+      *seed_ptr = seed;
+    }
+    if(state != prev)
+      *conv_ptr = state;
+  }
+}
+
+// ---------------------------------------------------------------- host side
+
+StagedMaps::StagedMaps()
+  : patch(0), ref_ptr(NULL), curr_ptr(NULL), ref_stride(0), curr_stride(0), width(0), height(0)
+{
+  memset(&maps, 0, sizeof(maps));
+}
+
+namespace
+{
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
+{
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = NULL;
+  static bool tried = false;
+  if(!tried)
+  {
+    tried = true;
+    void *p = NULL;
+    cudaDriverEntryPointQueryResult qres;
+    if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+       qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int encode_one(CUtensorMap *map, const void *base, int width, int height, int stride_floats,
+               int box_w, int box_h)
+{
+  PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+  if(!fn)
+    return fail(RMD_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)height};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride_floats * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
+                          box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if(res != CUDA_SUCCESS)
+  {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)res));
+    return RMD_ERR_INVALID_ARGUMENT;
+  }
+  return 0;
+}
+
+} // namespace
+
+int StagedMaps::encode(const FilterParams &P, int patch_side)
+{
+  if(((uintptr_t)P.ref % 16) != 0 || ((uintptr_t)P.curr % 16) != 0 || (P.ref_stride % 4) != 0 ||
+     (P.curr_stride % 4) != 0)
+    return fail(RMD_ERR_INVALID_ARGUMENT, "staged kernel: images must be 16-byte aligned with 16-byte pitch");
+  const bool geom_same = (width == P.width && height == P.height && patch == patch_side);
+  if(!(geom_same && ref_ptr == P.ref && ref_stride == P.ref_stride))
+  {
+    const int rc = encode_one(&maps.ref, P.ref, P.width, P.height, P.ref_stride, REF_BOX_W,
+                              ref_box_h(patch_side));
+    if(rc) return rc;
+    ref_ptr = P.ref; ref_stride = P.ref_stride;
+  }
+  if(!(geom_same && curr_ptr == P.curr && curr_stride == P.curr_stride))
+  {
+    for(int i = 0; i < NUM_WIDTHS; ++i)
+    {
+      const int rc = encode_one(&maps.curr[i], P.curr, P.width, P.height, P.curr_stride, strip_width(i),
+                                STRIP_BOX_ROWS);
+      if(rc) return rc;
+    }
+    curr_ptr = P.curr; curr_stride = P.curr_stride;
+  }
+  width = P.width; height = P.height; patch = patch_side;
+  return 0;
+}
+
+template<int PS>
+static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, cudaStream_t stream)
+{
+  static bool configured[64] = {false};
+  const size_t smem = sizeof(StagedSmem<PS>) + 128;  // slack for the manual 128-byte alignment
+  int device = 0;
+  cudaGetDevice(&device);
+  if(device < 0 || device >= 64 || !configured[device])
+  {
+    const cudaError_t err = cudaFuncSetAttribute(depth_filter_staged_kernel<PS>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if(err != cudaSuccess) return err;
+    if(device >= 0 && device < 64) configured[device] = true;
+  }
+  const dim3 block(TILE_W, TILE_H);
+  const dim3 grid((P.width + TILE_W - 1) / TILE_W, (P.height + TILE_H - 1) / TILE_H);
+  depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_depth_filter_staged(const FilterParams &P, const StagedMaps &maps, int patch_side,
+                                       cudaStream_t stream)
+{
+  if(patch_side == 5) return launch_staged<5>(P, maps, stream);
+  if(patch_side == 7) return launch_staged<7>(P, maps, stream);
+  return cudaErrorInvalidValue;
 }
 
 } // namespace rmdb

@@ -1,20 +1,31 @@
 """Parity of the sm_100a kernels (through the C-ABI) against the CPU oracle.
 
-Tolerances (floating point; stated here and in DESIGN.md "Tolerances"):
+The GPU path is compiled -use_fast_math like the reference (CMakeLists.txt:25);
+the oracle is IEEE fp32.  The two differ most in tau, the one-pixel
+triangulation uncertainty (src/triangulation.cu:53-68: z_plus - z cancels 3-4
+digits, so approximate sin/div move tau by ~1e-3 relative), which feeds sigma^2.
+Tolerances below were set from the spread MEASURED on a B200 between the oracle
+and the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref):
+tools/gpu_diag.py, profiles/r01_parity_spread.md.  They are the same spread:
+our kernels agree with the reference's CUDA build far more tightly (see
+test_ref_cuda_parity.py), so what is bounded here is IEEE-vs-fast-math.
+
   * seed initialisation: mu, sigma^2, a, b bit-exact; sum_templ <= 1e-5 and
     const_templ_denom <= 1e-3 absolute (the reference's own test tolerances,
     test/seed_matrix_test.cpp:148-149);
-  * one update from identical state: convergence states identical for
-    >= 99.5 % of the pixels; among pixels with identical state, |d mu| <=
-    1e-3 * depth_range and sigma^2, a, b within 1e-3 relative for >= 99 %;
-    best epipolar match within 1e-3 px for >= 99 % of the pixels matched by
-    both (a flipped arg-max between neighbouring 0.7 px candidates is the
-    remaining 1 %);
-  * sequences: same bars after 30 frames (differences do not accumulate: the
-    filter is contractive);
-  * denoiser vs the deterministic Jacobi oracle: max-abs <= 1e-4 * range;
+  * one update from bit-identical state: convergence states identical for
+    >= 99.9 % of the pixels; among those |d mu| <= 1e-3 * depth_range and
+    a, b within 1e-3 relative for >= 99.9 %, sigma^2 within 1e-2 relative for
+    >= 99 % (measured: mu p99.9 4e-6, a/b p99.9 2e-5, sigma^2 p99 1e-3..2e-3);
+    best match within 1e-3 px for >= 99.5 % (measured 99.96 %);
+  * 30-frame sequences (differences compound through the search interval
+    mu +- 3 sigma but stay bounded, the filter is contractive): states
+    identical >= 99 % (measured 99.7 %); median |d mu| <= 1e-3 * range and
+    >= 98 % within 1e-2 * range (measured median 2e-4, p99 3.5e-3); sigma^2
+    median relative <= 1e-2 and >= 97 % within 0.2; a, b >= 97 % within 0.05;
+  * denoiser vs the deterministic Jacobi oracle: max-abs <= 1e-4 * range
+    (measured 7e-6; the reference's own run-to-run spread is 1e-3..5e-2);
   * reductions: counts exact, float sum within 4 ulp of the double sum.
-The GPU path is compiled -use_fast_math like the reference; the oracle is IEEE.
 """
 import numpy as np
 import pytest
@@ -52,18 +63,37 @@ def _set_reference(seq, g, o):
     return f0, dmax - dmin
 
 
-def _assert_state_parity(g, o, depth_range, state_agree=0.995, frac_ok=0.99):
+def _field_stats(g, o, sel):
+    out = {}
+    for name, got, want in (("mu", g.downloadDepthmap(), o.mu), ("sigma_sq", g.downloadSigmaSq(), o.sigma_sq),
+                            ("a", g.downloadA(), o.a), ("b", g.downloadB(), o.b)):
+        d = np.abs(got.astype(np.float64) - want)[sel]
+        out[name] = (d, d / np.maximum(np.abs(want.astype(np.float64))[sel], 1e-12))
+    return out
+
+
+def _assert_single_frame_parity(g, o, depth_range):
+    """One update from bit-identical state (IEEE oracle vs fast-math GPU)."""
     conv_g, conv_o = g.downloadConvergence(), o.convergence
     same = conv_g == conv_o
-    assert same.mean() >= state_agree, f"state agreement {same.mean():.5f}"
-    interior = conv_o != ob.BORDER
-    sel = same & interior
-    d_mu = np.abs(g.downloadDepthmap().astype(np.float64) - o.mu)[sel]
-    assert (d_mu <= 1e-3 * depth_range).mean() >= frac_ok, f"mu: {(d_mu <= 1e-3 * depth_range).mean():.5f}"
-    for name, got, want in (("sigma_sq", g.downloadSigmaSq(), o.sigma_sq), ("a", g.downloadA(), o.a),
-                            ("b", g.downloadB(), o.b)):
-        rel = (np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-12))[sel]
-        assert (rel <= 1e-3).mean() >= frac_ok, f"{name}: {(rel <= 1e-3).mean():.5f}"
+    assert same.mean() >= 0.999, f"state agreement {same.mean():.5f}"
+    st = _field_stats(g, o, same & (conv_o != ob.BORDER))
+    assert (st["mu"][0] <= 1e-3 * depth_range).mean() >= 0.999
+    assert (st["a"][1] <= 1e-3).mean() >= 0.999 and (st["b"][1] <= 1e-3).mean() >= 0.999
+    assert (st["sigma_sq"][1] <= 1e-2).mean() >= 0.99, f"sigma_sq: {(st['sigma_sq'][1] <= 1e-2).mean():.5f}"
+
+
+def _assert_sequence_parity(g, o, depth_range):
+    """After a sequence (differences compound through mu +- 3 sigma)."""
+    conv_g, conv_o = g.downloadConvergence(), o.convergence
+    same = conv_g == conv_o
+    assert same.mean() >= 0.99, f"state agreement {same.mean():.5f}"
+    st = _field_stats(g, o, same & (conv_o != ob.BORDER))
+    assert np.median(st["mu"][0]) <= 1e-3 * depth_range
+    assert (st["mu"][0] <= 1e-2 * depth_range).mean() >= 0.98, f"mu: {(st['mu'][0] <= 1e-2 * depth_range).mean():.5f}"
+    assert np.median(st["sigma_sq"][1]) <= 1e-2
+    assert (st["sigma_sq"][1] <= 0.2).mean() >= 0.97
+    assert (st["a"][1] <= 0.05).mean() >= 0.97 and (st["b"][1] <= 0.05).mean() >= 0.97
 
 
 @pytest.mark.parametrize("patch", [5, 7])
@@ -92,10 +122,10 @@ def test_first_update_parity(small_sequence, variant):
     f = seq.frame(4, want_depth=False)
     g.update(f.image, f.T_cam_world)
     o.update(f.image, f.T_cam_world)
-    _assert_state_parity(g, o, rng_d)
+    _assert_single_frame_parity(g, o, rng_d)
     both = (g.downloadConvergence() == 0) & (o.convergence == 0)
     dm = np.abs(g.downloadEpipolarMatches() - o.matches).max(axis=2)[both]
-    assert (dm <= 1e-3).mean() >= 0.99
+    assert (dm <= 1e-3).mean() >= 0.995
     assert abs(g.getDistFromRef() - o.dist_from_ref()) < 1e-6
 
 
@@ -146,7 +176,7 @@ def test_update_from_uploaded_state(qvga_sequence, variant):
     f = seq.frame(13, want_depth=False)
     g.update(f.image, f.T_cam_world)
     o.update(f.image, f.T_cam_world)
-    _assert_state_parity(g, o, rng_d)
+    _assert_single_frame_parity(g, o, rng_d)
     assert g.getConvergedCount() == int((g.downloadConvergence() == 1).sum())
 
 
@@ -160,7 +190,7 @@ def test_sequence_parity_30_frames(qvga_sequence, variant):
         f = seq.frame(k, want_depth=False)
         g.update(f.image, f.T_cam_world)
         o.update(f.image, f.T_cam_world)
-    _assert_state_parity(g, o, rng_d, state_agree=0.99, frac_ok=0.985)
+    _assert_sequence_parity(g, o, rng_d)
     conv = g.downloadConvergence()
     c = conv == 1
     assert c.sum() > 0.5 * (seq.width - 2 * P) * (seq.height - 2 * P)
@@ -177,7 +207,7 @@ def test_patch7_sequence(small_sequence):
         f = seq.frame(k, want_depth=False)
         g.update(f.image, f.T_cam_world)
         o.update(f.image, f.T_cam_world)
-    _assert_state_parity(g, o, rng_d, state_agree=0.99, frac_ok=0.985)
+    _assert_sequence_parity(g, o, rng_d)
 
 
 def test_u8_and_depthmap_facade(small_sequence):

@@ -1,0 +1,190 @@
+"""Parity against the reference's OWN CUDA kernels rebuilt for sm_100a
+(oracle/_ref/librmd_ref*.so: /root/reference/src/{seed_matrix,depthmap_denoiser,
+reduction}.cu compiled unmodified, recipe oracle/Makefile).  Two roles:
+
+  1. it PINS the CPU oracle: the restatement in oracle/rmd_oracle.c must agree
+     with the code it restates (same tolerances as test_gpu_parity.py: what
+     separates them is IEEE vs -use_fast_math);
+  2. it is the north star's parity target for the product: "outputs must match
+     the reference CUDA path's depth and convergence maps within a stated float
+     tolerance".  Stated tolerance, from the spread measured on a B200
+     (profiles/r01_parity_spread.md): after a 30-frame sequence the convergence
+     maps agree for >= 99.9 % of the pixels, the depth (mu) is BIT-IDENTICAL for
+     >= 90 % of them and within 1e-3 * depth_range for >= 99 %; sigma^2 within
+     1e-2 relative and a, b within 1e-3 relative for >= 98.5 %.  The residue is
+     arg-max flips between neighbouring 0.7 px candidates (the texture unit's
+     filter arithmetic vs our FMA form differ in the last ulp).
+"""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import ref_binding as rb
+import rpg_open_remode_b200 as rmd
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not rb.available(5), reason="oracle/_ref not built (needs /root/reference at build time)")]
+
+FIELDS = (("mu", 0), ("sigma_sq", 1), ("a", 2), ("b", 3))
+VARIANTS = [pytest.param(rmd.VARIANT_DIRECT, id="direct"), pytest.param(rmd.VARIANT_STAGED, id="staged")]
+
+
+def _ours(seq, patch=5, variant=rmd.VARIANT_STAGED):
+    g = rmd.SeedMatrix(seq.width, seq.height, rmd.PinholeCamera(*seq.camera), patch_side=patch)
+    g.setOption(rmd.OPT_KERNEL_VARIANT, variant)
+    g.setOption(rmd.OPT_RECORD_MATCHES, 1)
+    return g
+
+
+def _snap_ours(g):
+    return {"conv": g.downloadConvergence(), "mu": g.downloadDepthmap(), "sigma_sq": g.downloadSigmaSq(),
+            "a": g.downloadA(), "b": g.downloadB()}
+
+
+def _snap_ref(r):
+    return {"conv": r.download(4), "mu": r.download(0), "sigma_sq": r.download(1), "a": r.download(2),
+            "b": r.download(3)}
+
+
+def _snap_oracle(o):
+    return {"conv": o.convergence.copy(), "mu": o.mu.copy(), "sigma_sq": o.sigma_sq.copy(), "a": o.a.copy(),
+            "b": o.b.copy()}
+
+
+def _assert_tight(A, B, depth_range, state=0.999, frac=0.985, identical=0.90):
+    same = A["conv"] == B["conv"]
+    assert same.mean() >= state, f"state agreement {same.mean():.5f}"
+    sel = same & (B["conv"] != 2)
+    d_mu = np.abs(A["mu"].astype(np.float64) - B["mu"])[sel]
+    assert (d_mu == 0).mean() >= identical, f"bit-identical mu: {(d_mu == 0).mean():.4f}"
+    assert (d_mu <= 1e-3 * depth_range).mean() >= 0.99
+    for name, tol in (("sigma_sq", 1e-2), ("a", 1e-3), ("b", 1e-3)):
+        rel = (np.abs(A[name].astype(np.float64) - B[name]) / np.maximum(np.abs(B[name]), 1e-12))[sel]
+        assert (rel <= tol).mean() >= frac, f"{name}: {(rel <= tol).mean():.5f}"
+
+
+def _run_three(seq, n_frames, patch=5, variant=rmd.VARIANT_STAGED, with_oracle=True):
+    f0 = seq.frame(0)
+    dmin, dmax = float(f0.depth.min()), float(f0.depth.max())
+    g = _ours(seq, patch, variant)
+    r = rb.RefSeeds(seq.width, seq.height, *seq.camera, patch=patch)
+    o = ob.OracleSeeds(seq.width, seq.height, *seq.camera, patch=patch) if with_oracle else None
+    g.setReferenceImage(f0.image, f0.T_cam_world, dmin, dmax)
+    r.set_reference(f0.image, f0.T_cam_world, dmin, dmax)
+    if o is not None:
+        o.set_reference(f0.image, f0.T_cam_world, dmin, dmax)
+    for k in range(1, n_frames + 1):
+        f = seq.frame(k, want_depth=False)
+        g.update(f.image, f.T_cam_world)
+        r.update(f.image, f.T_cam_world)
+        if o is not None:
+            o.update(f.image, f.T_cam_world)
+    return g, r, o, dmax - dmin, f0
+
+
+def test_oracle_is_pinned_by_reference_init(small_sequence):
+    """seedInitKernel (src/seed_init.cu) run by the reference itself vs the oracle."""
+    g, r, o, _, _ = _run_three(small_sequence, 0)
+    assert np.array_equal(r.download(0), o.mu) and np.array_equal(r.download(1), o.sigma_sq)
+    assert np.array_equal(r.download(2), o.a) and np.array_equal(r.download(3), o.b)
+    assert np.abs(r.download(5) - o.sum_templ).max() <= 1e-5
+    assert np.abs(r.download(6) - o.const_templ_denom).max() <= 1e-3
+    # and ours vs the reference: bit-exact
+    assert np.array_equal(g.downloadSumTempl(), r.download(5))
+    assert np.array_equal(g.downloadConstTemplDenom(), r.download(6))
+
+
+def test_oracle_is_pinned_by_reference_single_frame(qvga_sequence):
+    """One update of the reference's three kernels from state identical to the
+    oracle's: pins check + epipolar match + triangulation + Bayesian update."""
+    seq = qvga_sequence
+    g, r, o, rng_d, _ = _run_three(seq, 10)
+    so = _snap_oracle(o)
+    for name, fid in FIELDS:                       # everyone starts from the oracle's state
+        r.upload(fid, so[name])
+        g.uploadState(fid, so[name])
+    f = seq.frame(11, want_depth=False)
+    for x in (g, r):
+        x.update(f.image, f.T_cam_world)
+    o.update(f.image, f.T_cam_world)
+    sr, so, sg = _snap_ref(r), _snap_oracle(o), _snap_ours(g)
+    same = sr["conv"] == so["conv"]
+    assert same.mean() >= 0.999
+    sel = same & (so["conv"] != 2)
+    assert (np.abs(sr["mu"].astype(np.float64) - so["mu"])[sel] <= 1e-3 * rng_d).mean() >= 0.999
+    for name, tol, frac in (("sigma_sq", 1e-2, 0.99), ("a", 1e-3, 0.999), ("b", 1e-3, 0.999)):
+        rel = (np.abs(sr[name].astype(np.float64) - so[name]) / np.maximum(np.abs(so[name]), 1e-12))[sel]
+        assert (rel <= tol).mean() >= frac, name
+    both = (sr["conv"] == 0) & (so["conv"] == 0)
+    dm = np.abs(r.download(7) - o.matches).max(axis=2)[both]
+    assert (dm <= 1e-3).mean() >= 0.995
+    # ours vs the reference from the same state: essentially bit-identical
+    _assert_tight(sg, sr, rng_d, state=0.9995, frac=0.998, identical=0.995)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ours_matches_reference_cuda_sequence(qvga_sequence, variant):
+    g, r, _, rng_d, _ = _run_three(qvga_sequence, 30, variant=variant, with_oracle=False)
+    _assert_tight(_snap_ours(g), _snap_ref(r), rng_d)
+    assert g.getConvergedCount() == r.converged_count()
+    assert abs(g.getDistFromRef() - r.dist_from_ref()) < 1e-6
+
+
+def test_ours_matches_reference_cuda_vga_config1():
+    """BASELINE configs[0] stand-in: 30-frame VGA sequence, one keyframe."""
+    from rpg_open_remode_b200 import synth
+    seq = synth.SyntheticSequence(640, 480, seed=0x5EED0001)
+    g, r, _, rng_d, f0 = _run_three(seq, 30, with_oracle=False)
+    sg, sr = _snap_ours(g), _snap_ref(r)
+    _assert_tight(sg, sr, rng_d)
+    c = sg["conv"] == 1
+    assert c.mean() > 0.5
+    assert np.median(np.abs(sg["mu"] - f0.depth)[c]) < 0.01 * rng_d
+
+
+def test_ours_matches_reference_cuda_patch7(small_sequence):
+    if not rb.available(7):
+        pytest.skip("oracle/_ref/librmd_ref_p7.so not built")
+    g, r, _, rng_d, _ = _run_three(small_sequence, 12, patch=7, with_oracle=False)
+    _assert_tight(_snap_ours(g), _snap_ref(r), rng_d, state=0.998, frac=0.98, identical=0.85)
+
+
+def test_denoiser_vs_reference_cuda(qvga_sequence):
+    """The reference kernel is racy across 16x16 tile seams,
+    so it does not reproduce itself; ours is the deterministic Jacobi limit.
+    Bars: ours is at least as close to the reference as the reference's own
+    run-to-run spread allows -- median |diff| <= 1e-4 * range and 99 % of the
+    pixels within 2e-2 * range."""
+    seq = qvga_sequence
+    g, r, _, rng_d, _ = _run_three(seq, 15, with_oracle=False)
+    for fid in (0, 1, 2, 3):                        # identical input state
+        g.uploadState(fid, r.download(fid))
+    den = rmd.DepthmapDenoiser(seq.width, seq.height)
+    den.setLargeSigmaSq(rng_d)
+    rden = rb.RefDenoiser(seq.width, seq.height)
+    for iters in (50, 200):
+        mine = den.denoiseSeeds(g, 0.5, iters)
+        r1 = rden.run(r, rng_d, 0.5, iters)
+        r2 = rden.run(r, rng_d, 0.5, iters)
+        d = np.abs(mine - r1) / rng_d
+        spread = np.abs(r1 - r2).max() / rng_d
+        print(f"iters={iters}: ours-vs-ref median {np.median(d):.2e} p99 {np.percentile(d, 99):.2e} "
+              f"max {d.max():.2e}; reference run-to-run max {spread:.2e}")
+        assert np.median(d) <= 1e-4
+        assert np.percentile(d, 99) <= 2e-2
+
+
+def test_reductions_vs_reference_cuda():
+    rng = np.random.default_rng(12345)
+    img = rng.random((480, 752), dtype=np.float32)
+    ints = rng.integers(0, 256, size=(480, 752), dtype=np.int32)
+    d = rmd.DeviceImage(752, 480, "float32")
+    d.setDevData(img)
+    di = rmd.DeviceImage(752, 480, "int32")
+    di.setDevData(ints)
+    mine, ref = rmd.ImageReducer("float32").sum(d), rb.reduce_sum_f32(img)
+    exact = np.float32(img.astype(np.float64).sum())
+    ulp = np.spacing(exact)
+    assert abs(mine - exact) <= 4 * ulp and abs(ref - exact) <= 4 * ulp  # test/reduction_test.cpp:69
+    assert abs(ref - ob.sum_f32_ref_order(img)) <= 4 * ulp               # oracle restates the reference's order
+    assert rmd.ImageReducer("int32").countEqual(di, 2) == rb.reduce_count_eq(ints, 2) == int((ints == 2).sum())

@@ -82,6 +82,28 @@ int main()
     CK(cudaDestroyTextureObject(t));
   }
 
+  // ---- experiment 1y: the same staircase along y (texel rows by and by+1 hold 0 and 1)
+  {
+    const int by = 7;
+    std::fill(img.begin(), img.end(), 0.0f);
+    for(int x = 0; x < W; ++x) img[(by + 1) * W + x] = 1.0f;
+    cudaTextureObject_t t = make_tex();
+    const int N = 4096;
+    std::vector<float2> xy(N + 1);
+    for(int k = 0; k <= N; ++k) xy[k] = make_float2(10.5f, (float)by + 0.5f + (float)k / (float)N);
+    std::vector<float> out = run(t, xy);
+    int mism_round = 0, mism_floor = 0, levels = 0; float prev = -1.0f;
+    for(int k = 0; k < N; ++k)
+    {
+      const float fr = (float)k / (float)N;
+      mism_round += (out[k] != floorf(fr * 256.0f + 0.5f) / 256.0f);
+      mism_floor += (out[k] != floorf(fr * 256.0f) / 256.0f);
+      if(out[k] != prev) { prev = out[k]; ++levels; }
+    }
+    printf("EXP1y y-staircase: n_levels=%d mismatches vs round-half-up=%d vs floor=%d (of %d)\n", levels, mism_round, mism_floor, N);
+    CK(cudaDestroyTextureObject(t));
+  }
+
   // ---- experiment 2: value arithmetic. texels t0=0.3, t1=0.9 in x; check result vs formulas
   {
     std::fill(img.begin(), img.end(), 0.0f);
@@ -135,6 +157,26 @@ int main()
     }
     printf("EXP3 2-D: max|hw - quantised-weight model|=%.3g  max|hw - exact-weight model|=%.3g  bit-equal 4-term=%d sep=%d of %zu\n",
            max_q, max_exact, eq4, eqsep, xy.size());
+    // error distribution of the quantised model and where the large errors sit
+    int n_small = 0, n_mid = 0, n_big = 0;
+    for(size_t k = 0; k < xy.size(); ++k)
+    {
+      const float xb = xy[k].x - 0.5f, yb = xy[k].y - 0.5f;
+      const float tx = floorf(xb * 256.0f + 0.5f), ty = floorf(yb * 256.0f + 0.5f);
+      const int i = (int)floorf(tx / 256.0f), j = (int)floorf(ty / 256.0f);
+      const float a = (tx - i * 256.0f) / 256.0f, b = (ty - j * 256.0f) / 256.0f;
+      const double q = (1.0 - a) * (1.0 - b) * img[j * W + i] + (double)a * (1.0 - b) * img[j * W + i + 1] +
+                       (1.0 - a) * (double)b * img[(j + 1) * W + i] + (double)a * b * img[(j + 1) * W + i + 1];
+      const double e = fabs(out[k] - q);
+      if(e < 1e-6) ++n_small; else if(e < 1e-4) ++n_mid; else
+      {
+        if(n_big < 12)
+          printf("EXP3 big err %.3g at x=%.6f y=%.6f  frac_x*256=%.4f frac_y*256=%.4f  hw=%.6f model=%.6f\n", e,
+                 xy[k].x, xy[k].y, (xb - floorf(xb)) * 256.0f, (yb - floorf(yb)) * 256.0f, out[k], q);
+        ++n_big;
+      }
+    }
+    printf("EXP3 quantised-model error histogram: <1e-6: %d  <1e-4: %d  >=1e-4: %d\n", n_small, n_mid, n_big);
     // ---- experiment 4: NaN / inf coordinates
     std::vector<float2> bad;
     bad.push_back(make_float2(nanf(""), nanf("")));
