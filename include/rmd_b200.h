@@ -70,7 +70,8 @@ enum rmd_field {
   RMD_FIELD_SUM_TEMPL = 5,         /* float   downloadSumTempl                :218 */
   RMD_FIELD_CONST_TEMPL_DENOM = 6, /* float   downloadConstTemplDenom         :222 */
   RMD_FIELD_EPIPOLAR_MATCHES = 7,  /* float2  downloadEpipolarMatches         :226 */
-  RMD_FIELD_REF_IMG = 8            /* float   the reference image as uploaded */
+  RMD_FIELD_REF_IMG = 8,           /* float   the reference image as uploaded */
+  RMD_FIELD_DEBUG_TIMELINE = 100   /* int64[8] per CTA, see RMD_OPT_DEBUG_TIMELINE */
 };
 
 enum rmd_seeds_option {
@@ -83,7 +84,12 @@ enum rmd_seeds_option {
   RMD_OPT_KERNEL_VARIANT = 1,
   /* fractional bits of the bilinear weights of the current-image taps
    * (8 = what the texture unit of the reference path uses; 0 = exact fp32). */
-  RMD_OPT_TEX_FRAC_BITS = 2
+  RMD_OPT_TEX_FRAC_BITS = 2,
+  /* debug: the staged kernel records 8 x int64 per CTA (clock64 at its phase
+   * boundaries, SM id, active seeds, work items); read them back with
+   * rmd_seeds_download(h, RMD_FIELD_DEBUG_TIMELINE, dst) where dst holds
+   * 8 * ceil(w/32) * ceil(h/8) int64 values. */
+  RMD_OPT_DEBUG_TIMELINE = 3
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

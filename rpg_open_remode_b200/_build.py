@@ -60,7 +60,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + log[-1])
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread",
                                                       ]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)

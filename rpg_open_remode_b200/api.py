@@ -35,7 +35,8 @@ class ConvergenceStates:
 
 FIELD_MU, FIELD_SIGMA_SQ, FIELD_A, FIELD_B, FIELD_CONVERGENCE = 0, 1, 2, 3, 4
 FIELD_SUM_TEMPL, FIELD_CONST_TEMPL_DENOM, FIELD_EPIPOLAR_MATCHES, FIELD_REF_IMG = 5, 6, 7, 8
-OPT_RECORD_MATCHES, OPT_KERNEL_VARIANT, OPT_TEX_FRAC_BITS = 0, 1, 2
+OPT_RECORD_MATCHES, OPT_KERNEL_VARIANT, OPT_TEX_FRAC_BITS, OPT_DEBUG_TIMELINE = 0, 1, 2, 3
+FIELD_DEBUG_TIMELINE = 100
 VARIANT_STAGED, VARIANT_DIRECT = 0, 1
 
 _f32 = np.float32
@@ -348,6 +349,13 @@ class SeedMatrix:
         if a.shape != (self.height_, self.width_):
             raise ValueError(f"frame must be ({self.height_}, {self.width_}), got {a.shape}")
         return a
+
+    def downloadTimeline(self):
+        """Debug (OPT_DEBUG_TIMELINE): int64[n_ctas, 8] of the last staged launch."""
+        n = ((self.width_ + 31) // 32) * ((self.height_ + 7) // 8)
+        out = np.empty((n, 8), np.int64)
+        check(self._L.rmd_seeds_download(self._h, FIELD_DEBUG_TIMELINE, out.ctypes.data), "SeedMatrix::downloadTimeline")
+        return out
 
     def _download(self, field):
         if field == FIELD_CONVERGENCE:

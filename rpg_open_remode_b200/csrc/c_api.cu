@@ -8,6 +8,7 @@
 // H2D transfer of frame k+1 overlaps the kernel of frame k, one fused launch
 // per frame and no device synchronisation inside update().
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -15,6 +16,7 @@
 #include <string>
 
 #include "denoiser.cuh"
+#include "host_copy.h"
 #include "depth_filter.cuh"
 #include "reduction.cuh"
 #include "rmd_common.cuh"
@@ -114,6 +116,7 @@ struct rmd_seeds
   bool trust_conv;
 
   bool record_matches;
+  long long *timeline; size_t timeline_bytes;   // RMD_OPT_DEBUG_TIMELINE
   int variant;            // 0 staged, 1 direct
   int tex_frac_bits;
 
@@ -123,6 +126,7 @@ struct rmd_seeds
   bool t_valid;
 
   StagedMaps *maps;
+  ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
 };
 
 namespace
@@ -173,9 +177,11 @@ void seeds_free(rmd_seeds *s)
   for(int i = 0; i < 6; ++i) cudaFree(s->planar[i]);
   cudaFree(s->dense_tmp);
   cudaFree(s->counters);
+  cudaFree(s->timeline);
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
+  delete s->copier;
   cudaGetLastError();
 }
 
@@ -260,6 +266,7 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   P.trust_conv = s->trust_conv ? 1 : 0;
   P.converged_now = s->counters + (s->frame_index & 1);
   P.converged_next = s->counters + ((s->frame_index + 1) & 1);
+  P.timeline = s->timeline;
 
   if(s->timing) RMD_CUDA_TRY(cudaEventRecord(s->t0, s->stream));
   if(s->variant == 0)
@@ -293,7 +300,15 @@ int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *
   const size_t row_bytes = elem_size * (size_t)s->width;
   if(s->slot_used[slot])
     RMD_CUDA_TRY(cudaEventSynchronize(s->copied[slot]));  // pinned buffer free again
-  memcpy(s->pinned[slot], host_img, row_bytes * s->height);
+  if(!s->copier)
+  {
+    const char *env = getenv("RMD_COPY_THREADS");   // helper threads for the ingest copy (default 3)
+    int helpers = env ? atoi(env) : 3;
+    if(helpers < 0) helpers = 0;
+    if(helpers > 15) helpers = 15;
+    s->copier = new ParallelCopier(helpers);
+  }
+  s->copier->copy(s->pinned[slot], host_img, row_bytes * s->height);
   if(s->slot_used[slot])
     RMD_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->consumed[slot], 0));
   if(elem_size == sizeof(float))
@@ -436,6 +451,23 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     RMD_REQUIRE(value == 0 || value == 1, "RMD_OPT_KERNEL_VARIANT: 0 (staged) or 1 (direct)");
     s->variant = value;
     return 0;
+  case RMD_OPT_DEBUG_TIMELINE:
+  {
+    DeviceGuard guard(s->device);
+    if(value && !s->timeline)
+    {
+      s->timeline_bytes = sizeof(long long) * 8 * (size_t)((s->width + 31) / 32) * (size_t)((s->height + 7) / 8);
+      RMD_CUDA_TRY(cudaMalloc(&s->timeline, s->timeline_bytes));
+      RMD_CUDA_TRY(cudaMemset(s->timeline, 0, s->timeline_bytes));
+    }
+    else if(!value && s->timeline)
+    {
+      RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+      cudaFree(s->timeline);
+      s->timeline = NULL;
+    }
+    return 0;
+  }
   case RMD_OPT_TEX_FRAC_BITS:
     RMD_REQUIRE(value >= 0 && value <= 12, "RMD_OPT_TEX_FRAC_BITS: 0..12");
     s->tex_frac_bits = value;
@@ -584,6 +616,12 @@ int rmd_seeds_download(rmd_seeds_t *s, int field, void *host_dst)
                   "rmd_seeds_download: matches are only kept with RMD_OPT_RECORD_MATCHES");
     RMD_CUDA_TRY(cudaMemcpy2DAsync(host_dst, sizeof(float2) * w, s->matches, s->matches_pitch,
                                    sizeof(float2) * w, h, cudaMemcpyDeviceToHost, s->stream));
+  }
+  else if(field == RMD_FIELD_DEBUG_TIMELINE)
+  {
+    if(!s->timeline)
+      return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_download: RMD_OPT_DEBUG_TIMELINE is off");
+    RMD_CUDA_TRY(cudaMemcpyAsync(host_dst, s->timeline, s->timeline_bytes, cudaMemcpyDeviceToHost, s->stream));
   }
   else if(field == RMD_FIELD_REF_IMG)
   {

@@ -1,6 +1,7 @@
 // depth_filter_staged.cu -- fused depth filter, staged variant for sm_100a.
 //
-// One CTA = 32x8 pixels of the reference view (one warp per row).  Per frame:
+// One CTA = 32x2 pixels of the reference view (one warp per row; small CTAs so
+// that clusters of unconverged seeds spread over all SMs).  Per frame:
 //   0. classify every seed (convergence check, src/seed_check.cu:29-67);
 //      CTAs without a seed left to update stop here after 4 B/pixel;
 //   1. every active seed projects its depth interval into the current frame
@@ -48,8 +49,10 @@ struct __align__(128) StagedSmem
 {
   float strip[STRIP_FLOATS];
   float ref[REF_BOX_W * ref_box_h(PS)];
-  SearchRec rec[NTHREADS];
-  unsigned long long best[NTHREADS];
+  SearchRec rec[NPIX];
+  unsigned long long best[NPIX];
+  int level_total[TILE_H];
+  float l_checkpoint[NPIX][L_CHECKPOINTS];  // l of candidates 0, 16, 32, ... of every seed
   unsigned int level_mask[TILE_H][MAX_CHUNKS + 2];
   int level_cum[TILE_H][MAX_CHUNKS + 2];
   int bbox[4];       // xmin, ymin, xmax, ymax over all segments of the CTA
@@ -135,16 +138,46 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     const __grid_constant__ FilterParams P, const __grid_constant__ StagedTensorMaps M)
 {
   extern __shared__ unsigned char smem_raw[];
-  StagedSmem<PS> &S = *reinterpret_cast<StagedSmem<PS>*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  // 128-byte alignment for the TMA destinations, derived as an offset from
+  // smem_raw so that the compiler keeps the shared address space (LDS/STS).
+  const unsigned int smem_pad = (128u - (smem_addr(smem_raw) & 127u)) & 127u;
+  StagedSmem<PS> &S = *reinterpret_cast<StagedSmem<PS>*>(smem_raw + smem_pad);
 
-  const int lane = threadIdx.x, warp = threadIdx.y;
-  const int tid = warp * TILE_W + lane;
+  // GROUPS warps per pixel row: warp (row, 0) owns the row's 32 seeds
+  // (classification, search set-up, final update); all GROUPS warps of the row
+  // share its candidate work list, so a row full of unconverged seeds keeps
+  // 4 x 32 lanes busy instead of 32.
+  const int lane = threadIdx.x, wid = threadIdx.y;
+  const int row = wid / GROUPS, grp = wid % GROUPS;
+  const int tid = wid * TILE_W + lane;
+  const int pix = row * TILE_W + lane;
+  const bool owner = (grp == 0);
   const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
-  const int x = x0 + lane, y = y0 + warp;
+  const int x = x0 + lane, y = y0 + row;
 
   if(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
     *P.converged_next = 0u;
+
+  // debug timeline (RMD_OPT_DEBUG_TIMELINE): clock64 at phase boundaries
+  long long *const stamps =
+      P.timeline ? P.timeline + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  // [0] globaltimer ns at start, [1..4] SM cycles since start after classification /
+  // search set-up / TMA arrival / NCC search, [5] globaltimer ns at the end,
+  // [6] SM id, [7] work items of the CTA
+  const long long stamp_t0 = stamps ? clock64() : 0;
+#define RMD_STAMP(i) do { if(stamps && tid == 0) { if((i) == 5) { long long gt_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[5] = gt_; } \
+    else stamps[i] = clock64() - stamp_t0; } } while(0)
+  if(stamps && tid == 0)
+  {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    stamps[6] = (long long)smid;
+    stamps[7] = 0;
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    stamps[0] = gt;
+  }
 
   // ---- 0. classification
   bool active = false, converged = false;
@@ -152,7 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   int *conv_ptr = nullptr;
   float4 *seed_ptr = nullptr;
   float4 seed = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool inside = (x < P.width) && (y < P.height);
+  const bool inside = owner && (x < P.width) && (y < P.height);
   if(inside)
   {
     conv_ptr = P.conv + (size_t)y * P.conv_stride + x;
@@ -188,18 +221,42 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   }
   const int n_active = __syncthreads_count(active);
   if(n_active == 0)
+  {
+    if(stamps && tid == 0) stamps[1] = -(clock64() - stamp_t0);
     return;
+  }
+  RMD_STAMP(1);
 
   // ---- 1. search segments, candidate counts, bounding box
   EpiSegment seg;
   seg.mean = make_float2(0.f, 0.f); seg.dir = make_float2(0.f, 0.f); seg.half_len = 0.f;
-  int n_cand = 0;
+  int n_cand = 0, k_lo = INT_MAX, k_hi = -1;  // candidates, first / last one inside the image
   int bx_lo = INT_MAX, by_lo = INT_MAX, bx_hi = INT_MIN, by_hi = INT_MIN;
   if(active)
   {
     seg = epipolar_segment(P, x, y, seed.x, seed.y);
-    for(float l = -seg.half_len; l <= seg.half_len; l += RMD_EPIPOLAR_STEP)
-      ++n_cand;
+    // One pass over the seed's candidate positions, with the reference's own
+    // float accumulation of l (epipolar_match.cu:88): counts them, records l
+    // every 16th candidate (work items and the final match restart from
+    // there, bit-identically) and finds the contiguous range [k_lo, k_hi] that
+    // passes the image-bounds test (:91-97).  The segment is a straight line
+    // and the accepted region convex, so candidates outside the range can be
+    // skipped wholesale -- seeds whose projection left the image cost no items.
+    {
+      int k = 0;
+      for(float l = -seg.half_len; l <= seg.half_len; l += RMD_EPIPOLAR_STEP, ++k)
+      {
+        if((k & (L_CHECKPOINT_STEP - 1)) == 0)
+          S.l_checkpoint[pix][k / L_CHECKPOINT_STEP] = l;
+        const float2 px = make_float2(seg.mean.x + l * seg.dir.x, seg.mean.y + l * seg.dir.y);
+        if(!candidate_rejected<PS>(px, P.width, P.height))
+        {
+          k_lo = min(k_lo, k);
+          k_hi = k;
+        }
+      }
+      n_cand = k;
+    }
     const float ex0 = seg.mean.x - seg.half_len * seg.dir.x, ex1 = seg.mean.x + seg.half_len * seg.dir.x;
     const float ey0 = seg.mean.y - seg.half_len * seg.dir.y, ey1 = seg.mean.y + seg.half_len * seg.dir.y;
     int xl = to_int_clamped(floorf(fminf(ex0, ex1))) - (PS / 2 + 1);
@@ -209,18 +266,19 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     // only the part where candidates are accepted matters (epipolar_match.cu:91-97)
     xl = max(xl, PS - PS / 2 - 1); yl = max(yl, PS - PS / 2 - 1);
     xh = min(xh, P.width - 1);     yh = min(yh, P.height - 1);
-    if(n_cand > 0 && xl <= xh && yl <= yh)
+    if(k_hi >= 0 && xl <= xh && yl <= yh)
     {
       bx_lo = xl; bx_hi = xh; by_lo = yl; by_hi = yh;
     }
     const float2 stats = __ldg(P.templ + (size_t)y * P.templ_stride + x);
     SearchRec r;
     r.mean_x = seg.mean.x; r.mean_y = seg.mean.y; r.dir_x = seg.dir.x; r.dir_y = seg.dir.y;
-    r.half_len = seg.half_len; r.sum_templ = stats.x; r.denom = stats.y; r.n = n_cand;
-    S.rec[tid] = r;
+    r.half_len = seg.half_len; r.sum_templ = stats.x; r.denom = stats.y; r.n = (k_hi >= 0) ? (k_lo / CHUNK) : 0;  // first chunk with an accepted candidate
+    S.rec[pix] = r;
   }
   const unsigned long long kNoMatch = ((unsigned long long)orderable(-1.0f)) << 32;
-  S.best[tid] = kNoMatch;
+  if(owner)
+    S.best[pix] = kNoMatch;
   bx_lo = __reduce_min_sync(0xffffffffu, bx_lo); by_lo = __reduce_min_sync(0xffffffffu, by_lo);
   bx_hi = __reduce_max_sync(0xffffffffu, bx_hi); by_hi = __reduce_max_sync(0xffffffffu, by_hi);
   if(lane == 0 && bx_lo <= bx_hi)
@@ -230,6 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   }
   __syncthreads();
 
+  RMD_STAMP(2);
   // ---- 2. TMA: reference tile and current-image strip -> shared memory
   if(tid == 0)
   {
@@ -237,7 +296,11 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     int ox = 0, oy = 0, sw = 0, rows = 0, wi = 0;
     if(xmin <= xmax && ymin <= ymax)
     {
-      const int bw = xmax - xmin + 1, bh = ymax - ymin + 1;
+      // The TMA unit faults ("illegal instruction") when a box starts at a
+      // global address that is not 16-byte aligned (measured on B200,
+      // tools/tma_probe.cu): box origins are multiples of 4 floats.
+      const int xmin_a = xmin & ~3;
+      const int bw = xmax - xmin_a + 1, bh = ymax - ymin + 1;
       wi = NUM_WIDTHS - 1;
 #pragma unroll
       for(int i = NUM_WIDTHS - 1; i >= 0; --i)
@@ -246,67 +309,86 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       const int max_rows = (STRIP_FLOATS / sw) / STRIP_BOX_ROWS * STRIP_BOX_ROWS;
       const int want_rows = (bh + STRIP_BOX_ROWS - 1) / STRIP_BOX_ROWS * STRIP_BOX_ROWS;
       rows = min(want_rows, max_rows);
-      ox = (bw <= sw) ? xmin : xmin + (bw - sw) / 2;
+      ox = (bw <= sw) ? xmin_a : ((xmin_a + (bw - sw) / 2) & ~3);
       oy = (want_rows <= max_rows) ? ymin : ymin + (bh - rows) / 2;
     }
     S.strip_ox = ox; S.strip_oy = oy; S.strip_w = sw; S.strip_rows = rows;
     const unsigned int ref_bytes = REF_BOX_W * ref_box_h(PS) * (unsigned int)sizeof(float);
     mbar_expect_tx(&S.mbar, ref_bytes + (unsigned int)(rows * sw) * (unsigned int)sizeof(float));
-    tma_load_2d(S.ref, &M.ref, x0 - PS / 2, y0 - PS / 2, &S.mbar);
+    tma_load_2d(S.ref, &M.ref, x0 - REF_ORIGIN_X, y0 - PS / 2, &S.mbar);
     const CUtensorMap *cm = &M.curr[wi];
     for(int r = 0; r < rows; r += STRIP_BOX_ROWS)
       tma_load_2d(S.strip + r * sw, cm, ox, oy + r, &S.mbar);
   }
-  __syncthreads();
-  const int strip_ox = S.strip_ox, strip_oy = S.strip_oy, strip_w = S.strip_w, strip_rows = S.strip_rows;
-  mbar_wait(&S.mbar, 0);
 
-  // ---- 3. balanced NCC search: chunk-major work list per warp
+  // ---- 3. balanced NCC search: chunk-major work list per pixel row
+  if(owner)
   {
-    const int m = (n_cand + CHUNK - 1) / CHUNK;  // chunks of my seed (0 if inactive)
-    unsigned int my_mask = 0u;
-#pragma unroll
+    // level c of a row = the seeds that still have a c-th chunk of candidates;
+    // ballots are warp-uniform, so every lane tracks the running item count
+    const int m = (k_hi >= 0) ? (k_hi / CHUNK - k_lo / CHUNK + 1) : 0;  // chunks with accepted candidates
+    int cum = 0;
     for(int c = 0; c < MAX_CHUNKS; ++c)
     {
       const unsigned int mk = __ballot_sync(0xffffffffu, m > c);
-      if(lane == c) my_mask = mk;
+      if(lane == 0)
+      {
+        S.level_mask[row][c] = mk;
+        S.level_cum[row][c] = cum;  // items before level c
+      }
+      cum += __popc(mk);
     }
-    const int cnt = __popc(my_mask);
-    int inc = cnt;
+    if(lane == 0)
+    {
+      S.level_cum[row][MAX_CHUNKS] = cum;
+      S.level_total[row] = cum;
+    }
+    if(stamps && lane == 0) atomicAdd((unsigned long long*)&stamps[7], (unsigned long long)cum);
+  }
+  __syncthreads();  // publishes the work lists and the strip geometry (built while the TMA is in flight)
+  const int strip_ox = S.strip_ox, strip_oy = S.strip_oy, strip_w = S.strip_w, strip_rows = S.strip_rows;
+  mbar_wait(&S.mbar, 0);
+  RMD_STAMP(3);
+  // All warps of the CTA take 32-item rounds of the rows' lists round-robin.
+  for(int rho = wid; ; rho += NWARPS)
+  {
+    int r = 0, local = rho;
 #pragma unroll
-    for(int off = 1; off < 32; off <<= 1)
+    for(int k = 0; k < TILE_H - 1; ++k)
     {
-      const int v = __shfl_up_sync(0xffffffffu, inc, off);
-      if(lane >= off) inc += v;
+      const int rounds_k = (S.level_total[k] + 31) >> 5;
+      if(r == k && local >= rounds_k) { local -= rounds_k; r = k + 1; }
     }
-    const int total = __shfl_sync(0xffffffffu, inc, 31);
-    if(lane < MAX_CHUNKS + 2)
+    const int total = S.level_total[r];
+    if(local * 32 >= total)
+      break;
+    const int q = local * 32 + lane;
+    if(q < total)
     {
-      S.level_mask[warp][lane] = my_mask;
-      S.level_cum[warp][lane] = inc - cnt;  // items before level `lane`
-    }
-    __syncwarp();
+      // largest level c with level_cum[c] <= q (level_cum[MAX_CHUNKS] = total > q)
+      int c = 0, hi = MAX_CHUNKS;
+#pragma unroll
+      for(int step = 0; step < 6; ++step)
+      {
+        const int mid = (c + hi) >> 1;
+        if(S.level_cum[r][mid] <= q) c = mid; else hi = mid;
+      }
+      const int rank = q - S.level_cum[r][c];
+      const int src = __fns(S.level_mask[r][c], 0, rank + 1);  // lane owning the seed
 
-    for(int q = lane; q < total; q += 32)
-    {
-      int c = 0;
-      while(c + 1 < MAX_CHUNKS && S.level_cum[warp][c + 1] <= q) ++c;
-      const int rank = q - S.level_cum[warp][c];
-      const int src = __fns(S.level_mask[warp][c], 0, rank + 1);  // lane owning the seed
-
-      const SearchRec R = S.rec[warp * TILE_W + src];
+      const SearchRec R = S.rec[r * TILE_W + src];
       float templ[PS * PS];
 #pragma unroll
       for(int j = 0; j < PS; ++j)
 #pragma unroll
         for(int i = 0; i < PS; ++i)
-          templ[j * PS + i] = S.ref[(warp + j) * REF_BOX_W + src + i];
+          templ[j * PS + i] = S.ref[(r + j) * REF_BOX_W + src + i + (REF_ORIGIN_X - PS / 2)];
 
       // l of the chunk's first candidate: the same float accumulation as the
       // reference's loop (epipolar_match.cu:88), so positions are bit-identical
-      float l = -R.half_len;
-      const int first = c * CHUNK;
-      for(int k = 0; k < first; ++k) l += RMD_EPIPOLAR_STEP;
+      const int first = (R.n + c) * CHUNK;
+      float l = S.l_checkpoint[r * TILE_W + src][first / L_CHECKPOINT_STEP];
+      for(int k = 0; k < (first & (L_CHECKPOINT_STEP - 1)); ++k) l += RMD_EPIPOLAR_STEP;
 
       float best_ncc = -1.0f;
       int best_idx = 0;
@@ -341,16 +423,17 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       {
         const unsigned long long key =
             (((unsigned long long)orderable(best_ncc)) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)best_idx);
-        atomicMax(&S.best[warp * TILE_W + src], key);
+        atomicMax(&S.best[r * TILE_W + src], key);
       }
     }
-    __syncwarp();
   }
+  __syncthreads();
 
+  RMD_STAMP(4);
   // ---- 4. triangulation + Bayesian update by the owner of the seed
   if(active)
   {
-    const unsigned long long key = S.best[tid];
+    const unsigned long long key = S.best[pix];
     if(key == kNoMatch || !(n_cand > 0))
     {
       state = RMD_NO_MATCH;
@@ -366,8 +449,8 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       else
       {
         const int best_idx = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull));
-        float l = -seg.half_len;
-        for(int k = 0; k < best_idx; ++k) l += RMD_EPIPOLAR_STEP;
+        float l = S.l_checkpoint[pix][best_idx / L_CHECKPOINT_STEP];
+        for(int k = 0; k < (best_idx & (L_CHECKPOINT_STEP - 1)); ++k) l += RMD_EPIPOLAR_STEP;
         const float2 best_px = make_float2(seg.mean.x + l * seg.dir.x, seg.mean.y + l * seg.dir.y);
         if(P.matches)
           P.matches[(size_t)y * P.match_stride + x] = best_px;
@@ -383,6 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     if(state != prev)
       *conv_ptr = state;
   }
+  RMD_STAMP(5);
 }
 
 // ---------------------------------------------------------------- host side
@@ -476,7 +560,7 @@ static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, 
     if(err != cudaSuccess) return err;
     if(device >= 0 && device < 64) configured[device] = true;
   }
-  const dim3 block(TILE_W, TILE_H);
+  const dim3 block(TILE_W, NWARPS);
   const dim3 grid((P.width + TILE_W - 1) / TILE_W, (P.height + TILE_H - 1) / TILE_H);
   depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);
   return cudaGetLastError();

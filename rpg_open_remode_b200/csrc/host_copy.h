@@ -1,0 +1,149 @@
+// host_copy.h -- multi-threaded host memcpy for frame ingest.
+//
+// update() must return with the caller's (pageable) frame buffer reusable, as
+// the reference's synchronous cudaMemcpy2D guarantees
+// (include/rmd/device_image.cuh:93-106), so the frame is first copied into a
+// pinned ring slot.  One core copies a 1.2 MB VGA float frame in ~100 us, which
+// would cap end-to-end throughput well below the kernel's; a few helper
+// threads bring that to ~25 us.  Helpers spin briefly between frames (a
+// streaming sequence delivers one every few tens of microseconds) and sleep on
+// a condition variable when the stream pauses.
+#pragma once
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace rmdb
+{
+
+class ParallelCopier
+{
+public:
+  explicit ParallelCopier(int helpers) : generation_(0), pending_(0), stop_(false)
+  {
+    for(int i = 0; i < helpers; ++i)
+      threads_.emplace_back(&ParallelCopier::worker, this, i);
+  }
+
+  ~ParallelCopier()
+  {
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      stop_ = true;
+      generation_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    for(std::thread &t : threads_) t.join();
+  }
+
+  // Copies `bytes` from src to dst using the helpers plus the calling thread.
+  // Whether helpers pay off depends on the host (core count, CPU quota of the
+  // container): the first calls time both ways and the faster one is kept.
+  void copy(void *dst, const void *src, size_t bytes)
+  {
+    bool parallel = use_parallel_;
+    if(calibration_calls_ < kCalibrationCalls)
+      parallel = (calibration_calls_ & 1) != 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    copy_impl(dst, src, bytes, parallel && !threads_.empty() && bytes >= (256u << 10));
+    if(calibration_calls_ < kCalibrationCalls)
+    {
+      const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+      double &best = parallel ? best_parallel_us_ : best_single_us_;
+      if(calibration_calls_ >= 2 && us < best) best = us;   // the first call of each mode is a warm-up
+      if(++calibration_calls_ == kCalibrationCalls)
+        use_parallel_ = best_parallel_us_ < 0.8 * best_single_us_;
+    }
+  }
+
+  bool parallel_chosen() const { return use_parallel_; }
+
+private:
+  void copy_impl(void *dst, const void *src, size_t bytes, bool parallel)
+  {
+    const size_t parts = threads_.size() + 1;
+    if(!parallel)
+    {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t chunk = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
+    dst_ = static_cast<char*>(dst);
+    src_ = static_cast<const char*>(src);
+    bytes_ = bytes;
+    chunk_ = chunk;
+    pending_.store((int)threads_.size(), std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      generation_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    copy_part(threads_.size());  // the caller takes the last part
+    while(pending_.load(std::memory_order_acquire) != 0)
+      spin_pause();
+  }
+
+  static void spin_pause()
+  {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+  }
+
+  void copy_part(size_t index)
+  {
+    const size_t begin = index * chunk_;
+    if(begin >= bytes_) return;
+    const size_t n = (begin + chunk_ <= bytes_) ? chunk_ : bytes_ - begin;
+    memcpy(dst_ + begin, src_ + begin, n);
+  }
+
+  void worker(int index)
+  {
+    unsigned long long seen = 0;
+    for(;;)
+    {
+      // spin for ~100 us, then sleep until the next job
+      const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(100);
+      unsigned long long now = generation_.load(std::memory_order_acquire);
+      while(now == seen && std::chrono::steady_clock::now() < spin_until)
+      {
+        spin_pause();
+        now = generation_.load(std::memory_order_acquire);
+      }
+      if(now == seen)
+      {
+        std::unique_lock<std::mutex> lock(mutex_);
+        cv_.wait(lock, [&] { return generation_.load(std::memory_order_acquire) != seen; });
+        now = generation_.load(std::memory_order_acquire);
+      }
+      seen = now;
+      if(stop_) return;
+      copy_part((size_t)index);
+      pending_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+
+  static const int kCalibrationCalls = 12;
+  int calibration_calls_ = 0;
+  bool use_parallel_ = false;
+  double best_single_us_ = 1e30, best_parallel_us_ = 1e30;
+  std::vector<std::thread> threads_;
+  std::mutex mutex_;
+  std::condition_variable cv_;
+  std::atomic<unsigned long long> generation_;
+  std::atomic<int> pending_;
+  bool stop_;
+  char *dst_;
+  const char *src_;
+  size_t bytes_, chunk_;
+};
+
+} // namespace rmdb

@@ -100,6 +100,7 @@ struct FilterParams
   int trust_conv;       // 1: absorbing states recorded in conv are final
   unsigned int *converged_now;   // counter of this frame
   unsigned int *converged_next;  // counter to clear for the next frame
+  long long *timeline;           // debug: 8 clock64() stamps per CTA of the staged kernel, or null
 };
 
 } // namespace rmdb

@@ -12,17 +12,25 @@ namespace rmdb
 namespace staged
 {
 constexpr int TILE_W = 32;             // pixels per CTA row (one warp)
-constexpr int TILE_H = 8;              // rows per CTA (one per warp)
-constexpr int NTHREADS = TILE_W * TILE_H;
-constexpr int CHUNK = 8;               // candidates per work item
-constexpr int MAX_CHUNKS = 18;         // ceil(143 / CHUNK): 100 px / 0.7 px + 1 = 143 candidates
+constexpr int TILE_H = 8;              // pixel rows per CTA
+constexpr int GROUPS = 1;              // warps per pixel row (all warps share the CTA's work list)
+constexpr int NWARPS = TILE_H * GROUPS;
+constexpr int NTHREADS = 32 * NWARPS;
+constexpr int NPIX = TILE_W * TILE_H;  // seeds per CTA
+constexpr int CHUNK = 4;               // candidates per work item
+constexpr int MAX_CHUNKS = 36;         // ceil(143 / CHUNK): 100 px / 0.7 px + 1 = 143 candidates
 constexpr int STRIP_FLOATS = 10240;    // 40 KB current-image strip per CTA
+constexpr int L_CHECKPOINT_STEP = 16;   // l is stored every 16th candidate (power of two)
+constexpr int L_CHECKPOINTS = 9;        // ceil(143 / 16)
 constexpr int STRIP_BOX_ROWS = 8;      // rows per TMA box of the strip
-constexpr int REF_BOX_W = 40;          // >= TILE_W + 7 - 1, multiple of 4 floats (16 B)
+constexpr int REF_BOX_W = 40;          // covers [x0 - 4, x0 + 36): tile + halo of a 7x7 patch
+constexpr int REF_ORIGIN_X = 4;        // the reference box starts at x0 - 4 (16-byte aligned origin)
 constexpr int NUM_WIDTHS = 4;
 __host__ __device__ constexpr int strip_width(int i)
 {
-  return i == 0 ? 48 : (i == 1 ? 80 : (i == 2 ? 112 : 160));
+  // multiples of 32 floats: with one warp per pixel row, lanes read consecutive
+  // columns, so bank = column mod 32 is conflict-free whatever row a lane is on
+  return i == 0 ? 64 : (i == 1 ? 96 : (i == 2 ? 128 : 160));
 }
 __host__ __device__ constexpr int ref_box_h(int patch) { return TILE_H + patch - 1; }
 }

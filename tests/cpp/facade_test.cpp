@@ -210,7 +210,7 @@ int main()
       denoiser->denoise(seeds.getMu(), seeds.getSigmaSq(), seeds.getA(), seeds.getB(), out.data(), 0.5f, 5);
       CHECK(out[0] == -1.0f);
       denoiser->setLargeSigmaSq(dmax - dmin);
-      for(int k = 1; k <= 25; ++k)
+      for(int k = 1; k <= 30; ++k)
       {
         const Frame f = render(scene, W, H, k);
         seeds.update(const_cast<float*>(f.img.data()), f.T_world_cam.inv());
@@ -231,7 +231,7 @@ int main()
       for(float v : out) finite = finite && std::isfinite(v);
       CHECK(finite);
       const float pct = (float)seeds.getConvergedCount() / (float)(W * H) * 100.0f;  // depthmap.cpp:150-154
-      std::printf("converged %.1f %% after 25 frames, median error %.4f m\n", pct, errs[errs.size() / 2]);
+      std::printf("converged %.1f %% after 30 frames, median error %.4f m\n", pct, errs[errs.size() / 2]);
     }
     // ---- error convention: CUDA failures surface as rmd::CudaException
     {

@@ -1,0 +1,12 @@
+#!/bin/bash
+set -x
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "staged" > gpurun_out/pytest_staged.log 2>&1
+timeout 1500 python -m pytest tests/test_ref_cuda_parity.py -m gpu -q > gpurun_out/pytest_gpu_b.log 2>&1
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+timeout 900 python bench.py --variant staged --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_staged.json 2> gpurun_out/bench_staged.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 450 --csv --log-file gpurun_out/launches_staged.csv python bench.py --variant staged --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 5 -c 1 -o gpurun_out/prof_staged python bench.py --variant staged --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_staged.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 120 -c 1 -o gpurun_out/prof_staged_steady python bench.py --variant staged --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_staged_steady.log 2>&1
+echo done

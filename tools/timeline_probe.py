@@ -1,0 +1,48 @@
+"""Per-CTA timeline of the staged kernel at a steady-state and a heavy frame (GPU box)."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import rpg_open_remode_b200 as rmd
+from rpg_open_remode_b200 import synth
+
+W, H = 640, 480
+seq = synth.SyntheticSequence(W, H, seed=0x5EED0002)
+f0 = seq.frame(0)
+s = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera))
+s.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED)
+s.setOption(rmd.OPT_DEBUG_TIMELINE, 1)
+s.enableKernelTiming(True)
+s.setReferenceImage(f0.image, f0.T_cam_world, float(f0.depth.min()), float(f0.depth.max()))
+for k in range(1, 131):
+    f = seq.frame(k, want_depth=False)
+    s.update(f.image, f.T_cam_world)
+    if k in (4, 40, 130):
+        s.sync()
+        t = s.downloadTimeline()
+        ms = s.lastKernelMs()
+        act = t[:, 1] > 0
+        start = t[:, 0] - t[:, 0].min()
+        end = t[:, 5] - t[:, 0].min()
+        dur_ns = (t[:, 5] - t[:, 0])[act]
+        print(f"frame {k}: kernel {ms*1e3:.1f} us; CTAs {len(t)}, active {act.sum()}, items total {t[:,7].sum()}, "
+              f"span of starts {start.max()/1e3:.1f} us, last end {end[act].max()/1e3 if act.any() else 0:.1f} us")
+        if act.any():
+            ph = t[act][:, 1:5].astype(np.float64)
+            d = np.diff(np.concatenate([np.zeros((ph.shape[0], 1)), ph], axis=1), axis=1)
+            for name, col in zip(("classify", "setup", "tma+tables", "search"), d.T):
+                print(f"   {name:12s} cycles: median {np.median(col):8.0f}  p90 {np.percentile(col,90):8.0f}  max {col.max():8.0f}")
+            print(f"   active CTA duration ns: median {np.median(dur_ns):.0f} p90 {np.percentile(dur_ns,90):.0f} max {dur_ns.max():.0f}")
+            items = t[act][:, 7]
+            print(f"   items per active CTA: median {np.median(items):.0f} p90 {np.percentile(items,90):.0f} max {items.max()}")
+            # per-SM busy time
+            sm = t[:, 6]
+            busy = {}
+            for smid in np.unique(sm):
+                sel = sm == smid
+                busy[smid] = (end[sel].max() - start[sel].min()) / 1e3
+            b = np.array(list(busy.values()))
+            print(f"   per-SM first-start..last-end us: min {b.min():.1f} median {np.median(b):.1f} max {b.max():.1f}; CTAs/SM {len(t)/len(b):.1f}")
+            inact = ~act
+            if inact.any():
+                di = (t[:, 5] - t[:, 0])[inact] if False else None
