@@ -49,7 +49,7 @@ BYTES_PER_PIXEL_FUSED = 52  # SURVEY.md 8d / BASELINE.md 4: algorithmic bytes pe
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=640)
@@ -83,7 +83,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -148,6 +148,18 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_ncu_staged.json: heavy and steady frame); never measured under
+    the timed run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_staged.json")) as f:
+            t = json.load(f)["traffic_bytes_per_launch"]
+        return {"heavy_frame": t["heavy"], "steady_frame": t["steady"], "source": "profiles/r01_ncu_staged.md"}
+    except Exception:
+        return None
 
 
 def cpu_baseline(args, frames, poses, dmin, dmax, seq):
@@ -270,7 +282,8 @@ def run_ours(args, rank, world, local_rank):
     achieved = algo_bytes / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "kernel": "depth_filter_%s_kernel<%d>" % (variant, args.patch),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": (ncu_traffic() or {}).get("heavy_frame"),
+                "traffic_detail": ncu_traffic(),
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "avg_launch_us": avg_launch_s * 1e6,
                 "launch_us_min_median_max": [float(per_launch_ms.min() * 1e3), float(np.median(per_launch_ms) * 1e3),

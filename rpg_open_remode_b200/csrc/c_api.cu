@@ -126,6 +126,12 @@ struct rmd_seeds
   bool t_valid;
 
   StagedMaps *maps;
+  // busy-tile splitting of the staged kernel (depth_filter_staged.cu)
+  int n_tiles, cta_slots;
+  unsigned long long *tile_keys;
+  unsigned int *tile_arrivals;
+  int *tile_items[2];
+  unsigned int *frame_items;   // 3 rotating slots
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
 };
 
@@ -154,6 +160,17 @@ int seeds_alloc(rmd_seeds *s)
   RMD_CUDA_TRY(cudaMalloc(&s->counters, 2 * sizeof(unsigned int)));
   RMD_CUDA_TRY(cudaMemset(s->counters, 0, 2 * sizeof(unsigned int)));
   RMD_CUDA_TRY(cudaMemset2D(s->conv, s->conv_pitch, 0, sizeof(int) * (size_t)w, h));
+  {
+    s->n_tiles = ((w + staged::TILE_W - 1) / staged::TILE_W) * ((h + staged::TILE_H - 1) / staged::TILE_H);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    s->cta_slots = sms * 3;
+    RMD_CUDA_TRY(cudaMalloc(&s->tile_keys, sizeof(unsigned long long) * (size_t)s->n_tiles * staged::NPIX));
+    RMD_CUDA_TRY(cudaMalloc(&s->tile_arrivals, sizeof(unsigned int) * (size_t)s->n_tiles));
+    RMD_CUDA_TRY(cudaMalloc(&s->tile_items[0], sizeof(int) * (size_t)s->n_tiles));
+    RMD_CUDA_TRY(cudaMalloc(&s->tile_items[1], sizeof(int) * (size_t)s->n_tiles));
+    RMD_CUDA_TRY(cudaMalloc(&s->frame_items, 3 * sizeof(unsigned int)));
+  }
   RMD_CUDA_TRY(cudaEventCreate(&s->t0));
   RMD_CUDA_TRY(cudaEventCreate(&s->t1));
   return 0;
@@ -178,6 +195,8 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->dense_tmp);
   cudaFree(s->counters);
   cudaFree(s->timeline);
+  cudaFree(s->tile_keys); cudaFree(s->tile_arrivals); cudaFree(s->tile_items[0]); cudaFree(s->tile_items[1]);
+  cudaFree(s->frame_items);
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
@@ -226,6 +245,13 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   ip.avg_depth = s->avg_depth; ip.sigma_sq_max = s->sigma_sq_max;
   RMD_CUDA_TRY(launch_seed_init(ip, s->patch, s->stream));
   RMD_CUDA_TRY(cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned int), s->stream));
+  // no tile is split in the first frame of a keyframe; keys hold "no match"
+  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_items[0], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_items[1], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->frame_items, 0, 3 * sizeof(unsigned int), s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_arrivals, 0, sizeof(unsigned int) * (size_t)s->n_tiles, s->stream));
+  RMD_CUDA_TRY(launch_fill_u64(s->tile_keys, (size_t)s->n_tiles * staged::NPIX, 0x407FFFFF00000000ull, s->stream));
+  s->n_total += 1;
   s->n_total += 1;
   s->has_reference = true;
   s->frame_index = 0;
@@ -267,6 +293,18 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   P.converged_now = s->counters + (s->frame_index & 1);
   P.converged_next = s->counters + ((s->frame_index + 1) & 1);
   P.timeline = s->timeline;
+  {
+    const uint64_t f = s->frame_index;
+    P.split_max = staged::SPLIT_MAX;
+    P.cta_slots = s->cta_slots;
+    P.tile_keys = s->tile_keys;
+    P.tile_arrivals = s->tile_arrivals;
+    P.tile_items_prev = s->tile_items[(f + 1) & 1];
+    P.tile_items_next = s->tile_items[f & 1];
+    P.frame_items_prev = s->frame_items + ((f + 2) % 3);
+    P.frame_items_next = s->frame_items + (f % 3);
+    P.frame_items_zero = s->frame_items + ((f + 1) % 3);
+  }
 
   if(s->timing) RMD_CUDA_TRY(cudaEventRecord(s->t0, s->stream));
   if(s->variant == 0)

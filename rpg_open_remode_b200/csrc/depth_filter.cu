@@ -174,6 +174,12 @@ __global__ void __launch_bounds__(256) import_plane_kernel(
     dst[(size_t)y * dst_stride_floats + (size_t)x * comps + comp] = src[(size_t)y * src_stride + x];
 }
 
+__global__ void __launch_bounds__(256) fill_u64_kernel(unsigned long long *dst, size_t n, unsigned long long value)
+{
+  for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = value;
+}
+
 // ---------------------------------------------------------------- launchers
 
 static inline dim3 grid_for(int width, int height, dim3 block)
@@ -204,6 +210,13 @@ cudaError_t launch_depth_filter_direct(const FilterParams &P, int patch_side, cu
     depth_filter_direct_kernel<7><<<grid, block, 0, stream>>>(P);
   else
     return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream)
+{
+  const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  fill_u64_kernel<<<blocks > 0 ? blocks : 1, 256, 0, stream>>>(dst, n, value);
   return cudaGetLastError();
 }
 

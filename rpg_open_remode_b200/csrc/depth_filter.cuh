@@ -31,6 +31,9 @@ struct StagedMaps;
 cudaError_t launch_depth_filter_staged(const FilterParams &P, const StagedMaps &maps,
                                        int patch_side, cudaStream_t stream);
 
+// dst[i] = value for i < n (64-bit pattern fill)
+cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);
+
 cudaError_t launch_u8_to_float(const uint8_t *src, int src_stride, float *dst, int dst_stride,
                                int width, int height, cudaStream_t stream);
 cudaError_t launch_export_plane(const float *src, int src_stride_floats, int comps, int comp,

@@ -57,6 +57,7 @@ struct __align__(128) StagedSmem
   int level_cum[TILE_H][MAX_CHUNKS + 2];
   int bbox[4];       // xmin, ymin, xmax, ymax over all segments of the CTA
   int strip_ox, strip_oy, strip_w, strip_rows;
+  int is_last;
   unsigned long long mbar;
 };
 
@@ -143,27 +144,44 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   const unsigned int smem_pad = (128u - (smem_addr(smem_raw) & 127u)) & 127u;
   StagedSmem<PS> &S = *reinterpret_cast<StagedSmem<PS>*>(smem_raw + smem_pad);
 
-  // GROUPS warps per pixel row: warp (row, 0) owns the row's 32 seeds
-  // (classification, search set-up, final update); all GROUPS warps of the row
-  // share its candidate work list, so a row full of unconverged seeds keeps
-  // 4 x 32 lanes busy instead of 32.
-  const int lane = threadIdx.x, wid = threadIdx.y;
-  const int row = wid / GROUPS, grp = wid % GROUPS;
+  const int lane = threadIdx.x, wid = threadIdx.y;   // warp `wid` owns pixel row `wid` of the tile
   const int tid = wid * TILE_W + lane;
-  const int pix = row * TILE_W + lane;
-  const bool owner = (grp == 0);
+  const int pix = tid;
   const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
-  const int x = x0 + lane, y = y0 + row;
+  const int x = x0 + lane, y = y0 + wid;
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const int z = blockIdx.z;
 
-  if(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+  // ---- split factor of this tile.  A frame's duration is bounded below by its
+  // busiest tile (up to 9216 work items on one CTA) once most seeds have
+  // converged; tiles that were much busier than the per-slot average in the
+  // PREVIOUS frame are processed by zeff CTAs (blockIdx.z < zeff), each taking
+  // every zeff-th round of the work list.  All CTAs of a tile read the same
+  // two numbers, so they agree on zeff without talking to each other.
+  int zeff = 1;
+  if(gridDim.z > 1)
+  {
+    const int items_prev = P.tile_items_prev[tile];
+    const unsigned int avg_per_slot = *P.frame_items_prev / (unsigned int)P.cta_slots;
+    if(items_prev > SPLIT_MIN_ITEMS && (unsigned int)items_prev > 2u * avg_per_slot)
+      zeff = min((int)gridDim.z,
+                 (items_prev + SPLIT_ITEMS_PER_CTA - 1) / SPLIT_ITEMS_PER_CTA);
+    if(z >= zeff)
+      return;
+  }
+  const bool lead = (z == 0);  // the CTA that records what all of them compute identically
+
+  if(tile == 0 && lead && tid == 0)
+  {
     *P.converged_next = 0u;
+    *P.frame_items_zero = 0u;
+  }
 
-  // debug timeline (RMD_OPT_DEBUG_TIMELINE): clock64 at phase boundaries
-  long long *const stamps =
-      P.timeline ? P.timeline + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  // debug timeline (RMD_OPT_DEBUG_TIMELINE), lead CTA only:
   // [0] globaltimer ns at start, [1..4] SM cycles since start after classification /
   // search set-up / TMA arrival / NCC search, [5] globaltimer ns at the end,
-  // [6] SM id, [7] work items of the CTA
+  // [6] SM id, [7] work items of the tile
+  long long *const stamps = (P.timeline && lead) ? P.timeline + 8 * (size_t)tile : nullptr;
   const long long stamp_t0 = stamps ? clock64() : 0;
 #define RMD_STAMP(i) do { if(stamps && tid == 0) { if((i) == 5) { long long gt_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[5] = gt_; } \
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   int *conv_ptr = nullptr;
   float4 *seed_ptr = nullptr;
   float4 seed = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool inside = owner && (x < P.width) && (y < P.height);
+  const bool inside = (x < P.width) && (y < P.height);
   if(inside)
   {
     conv_ptr = P.conv + (size_t)y * P.conv_stride + x;
@@ -206,9 +224,10 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       active = (state == RMD_UPDATE);
     }
     converged = (state == RMD_CONVERGED);
-    if(!active && state != prev)
+    if(lead && !active && state != prev)
       *conv_ptr = state;
   }
+  if(lead)
   {
     const unsigned int ballot = __ballot_sync(0xffffffffu, converged);
     if(lane == 0 && ballot)
@@ -222,6 +241,8 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   const int n_active = __syncthreads_count(active);
   if(n_active == 0)
   {
+    if(lead && tid == 0 && gridDim.z > 1)
+      P.tile_items_next[tile] = 0;
     if(stamps && tid == 0) stamps[1] = -(clock64() - stamp_t0);
     return;
   }
@@ -273,12 +294,12 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     const float2 stats = __ldg(P.templ + (size_t)y * P.templ_stride + x);
     SearchRec r;
     r.mean_x = seg.mean.x; r.mean_y = seg.mean.y; r.dir_x = seg.dir.x; r.dir_y = seg.dir.y;
-    r.half_len = seg.half_len; r.sum_templ = stats.x; r.denom = stats.y; r.n = (k_hi >= 0) ? (k_lo / CHUNK) : 0;  // first chunk with an accepted candidate
+    r.half_len = seg.half_len; r.sum_templ = stats.x; r.denom = stats.y;
+    r.n = (k_hi >= 0) ? (k_lo / CHUNK) : 0;  // first chunk with an accepted candidate
     S.rec[pix] = r;
   }
   const unsigned long long kNoMatch = ((unsigned long long)orderable(-1.0f)) << 32;
-  if(owner)
-    S.best[pix] = kNoMatch;
+  S.best[pix] = kNoMatch;
   bx_lo = __reduce_min_sync(0xffffffffu, bx_lo); by_lo = __reduce_min_sync(0xffffffffu, by_lo);
   bx_hi = __reduce_max_sync(0xffffffffu, bx_hi); by_hi = __reduce_max_sync(0xffffffffu, by_hi);
   if(lane == 0 && bx_lo <= bx_hi)
@@ -322,7 +343,6 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   }
 
   // ---- 3. balanced NCC search: chunk-major work list per pixel row
-  if(owner)
   {
     // level c of a row = the seeds that still have a c-th chunk of candidates;
     // ballots are warp-uniform, so every lane tracks the running item count
@@ -333,24 +353,35 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       const unsigned int mk = __ballot_sync(0xffffffffu, m > c);
       if(lane == 0)
       {
-        S.level_mask[row][c] = mk;
-        S.level_cum[row][c] = cum;  // items before level c
+        S.level_mask[wid][c] = mk;
+        S.level_cum[wid][c] = cum;  // items before level c
       }
       cum += __popc(mk);
     }
     if(lane == 0)
     {
-      S.level_cum[row][MAX_CHUNKS] = cum;
-      S.level_total[row] = cum;
+      S.level_cum[wid][MAX_CHUNKS] = cum;
+      S.level_total[wid] = cum;
     }
-    if(stamps && lane == 0) atomicAdd((unsigned long long*)&stamps[7], (unsigned long long)cum);
   }
   __syncthreads();  // publishes the work lists and the strip geometry (built while the TMA is in flight)
+  if(lead && tid == 0 && (gridDim.z > 1 || stamps))
+  {
+    int items = 0;
+#pragma unroll
+    for(int k = 0; k < TILE_H; ++k) items += S.level_total[k];
+    if(gridDim.z > 1)
+    {
+      P.tile_items_next[tile] = items;
+      atomicAdd(P.frame_items_next, (unsigned int)items);
+    }
+    if(stamps) stamps[7] = items;
+  }
   const int strip_ox = S.strip_ox, strip_oy = S.strip_oy, strip_w = S.strip_w, strip_rows = S.strip_rows;
   mbar_wait(&S.mbar, 0);
   RMD_STAMP(3);
-  // All warps of the CTA take 32-item rounds of the rows' lists round-robin.
-  for(int rho = wid; ; rho += NWARPS)
+  // The warps of the tile's zeff CTAs take 32-item rounds of the rows' lists round-robin.
+  for(int rho = z * NWARPS + wid; ; rho += zeff * NWARPS)
   {
     int r = 0, local = rho;
 #pragma unroll
@@ -428,12 +459,36 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     }
   }
   __syncthreads();
-
   RMD_STAMP(4);
+
+  // ---- 3b. a split tile: merge the partial arg-max of its CTAs in global
+  // memory; the last CTA to arrive finalises the tile (and leaves the keys and
+  // the arrival counter reset for the next frame).
+  unsigned long long key = S.best[pix];
+  if(zeff > 1)
+  {
+    unsigned long long *gkey = P.tile_keys + (size_t)tile * NPIX + pix;
+    if(key != kNoMatch)
+      atomicMax(gkey, key);
+    __threadfence();
+    __syncthreads();
+    if(tid == 0)
+    {
+      const unsigned int ticket = atomicAdd(P.tile_arrivals + tile, 1u);
+      S.is_last = (ticket == (unsigned int)(zeff - 1)) ? 1 : 0;
+      if(S.is_last)
+        P.tile_arrivals[tile] = 0u;
+    }
+    __syncthreads();
+    if(!S.is_last)
+      return;
+    __threadfence();
+    key = atomicExch(gkey, kNoMatch);
+  }
+
   // ---- 4. triangulation + Bayesian update by the owner of the seed
   if(active)
   {
-    const unsigned long long key = S.best[pix];
     if(key == kNoMatch || !(n_cand > 0))
     {
       state = RMD_NO_MATCH;
@@ -561,8 +616,9 @@ static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, 
     if(device >= 0 && device < 64) configured[device] = true;
   }
   const dim3 block(TILE_W, NWARPS);
-  const dim3 grid((P.width + TILE_W - 1) / TILE_W, (P.height + TILE_H - 1) / TILE_H);
-  depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);
+  const dim3 grid((P.width + TILE_W - 1) / TILE_W, (P.height + TILE_H - 1) / TILE_H,
+                  P.split_max > 1 ? P.split_max : 1);
+  depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);  // grid.z = P.split_max
   return cudaGetLastError();
 }
 

@@ -101,6 +101,16 @@ struct FilterParams
   unsigned int *converged_now;   // counter of this frame
   unsigned int *converged_next;  // counter to clear for the next frame
   long long *timeline;           // debug: 8 clock64() stamps per CTA of the staged kernel, or null
+  // staged kernel, busy-tile splitting (depth_filter_staged.cu)
+  int split_max;                         // grid.z; 1 = never split
+  int cta_slots;                         // resident CTAs of the whole GPU (SMs x CTAs per SM)
+  unsigned long long *tile_keys;         // [tiles][256] partial arg-max keys of split tiles
+  unsigned int *tile_arrivals;           // [tiles] CTAs of a split tile that finished searching
+  const int *tile_items_prev;            // [tiles] work items of each tile in the previous frame
+  int *tile_items_next;                  // [tiles] ... written this frame
+  const unsigned int *frame_items_prev;  // work items of the whole previous frame
+  unsigned int *frame_items_next;        // ... accumulated this frame
+  unsigned int *frame_items_zero;        // slot to clear for the next frame
 };
 
 } // namespace rmdb
