@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--patch", type=int, default=5)
     ap.add_argument("--variant", default=None, choices=[None, "staged", "direct"])
-    ap.add_argument("--cpu-frames", type=int, default=6,
+    ap.add_argument("--cpu-frames", type=int, default=30,
                     help="bounded sample of the sequence for the CPU baseline (frames 1..n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-cpu", action="store_true",
@@ -409,10 +409,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: whatever libraries print on fd 1
+    # (e.g. "NCCL version ...") goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         out = run_reference(args, rank, world, local_rank)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
         return
     if world > 1:
         import torch
@@ -423,7 +432,7 @@ def main():
                                 device_id=torch.device("cuda", local_rank))
     out = run_ours(args, rank, world, local_rank)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -111,7 +111,9 @@ private:
     for(;;)
     {
       // spin for ~100 us, then sleep until the next job
-      const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(100);
+      // (2 ms: helpers stay hot at any frame rate above ~500 fps; a condition-variable
+      // wake-up costs more than the copy it would help with)
+      const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(2000);
       unsigned long long now = generation_.load(std::memory_order_acquire);
       while(now == seen && std::chrono::steady_clock::now() < spin_until)
       {
