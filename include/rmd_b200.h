@@ -89,7 +89,13 @@ enum rmd_seeds_option {
    * boundaries, SM id, active seeds, work items); read them back with
    * rmd_seeds_download(h, RMD_FIELD_DEBUG_TIMELINE, dst) where dst holds
    * 8 * ceil(w/32) * ceil(h/8) int64 values. */
-  RMD_OPT_DEBUG_TIMELINE = 3
+  RMD_OPT_DEBUG_TIMELINE = 3,
+  /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
+   * path (defaults in csrc/staged_maps.cuh); results never depend on them */
+  RMD_OPT_TUNE_SPLIT_MAX = 10,
+  RMD_OPT_TUNE_SPLIT_MIN_ITEMS = 11,
+  RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA = 12,
+  RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

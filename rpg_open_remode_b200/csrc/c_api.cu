@@ -132,6 +132,7 @@ struct rmd_seeds
   unsigned int *tile_arrivals;
   int *tile_items[2];
   unsigned int *frame_items;   // 3 rotating slots
+  int tune[4];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
 };
 
@@ -295,7 +296,8 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   P.timeline = s->timeline;
   {
     const uint64_t f = s->frame_index;
-    P.split_max = staged::SPLIT_MAX;
+    P.split_max = s->tune[0]; P.split_min_items = s->tune[1]; P.split_items_per_cta = s->tune[2];
+    P.sparse_max_seeds = s->tune[3];
     P.cta_slots = s->cta_slots;
     P.tile_keys = s->tile_keys;
     P.tile_arrivals = s->tile_arrivals;
@@ -442,6 +444,8 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->cam.fx = fx; s->cam.fy = fy; s->cam.cx = cx; s->cam.cy = cy;
   s->one_pix_angle = atan2f(1.0f, 2.0f * fx) * 2.0f;  // pinhole_camera.cuh:55-59
   s->tex_frac_bits = 8;
+  s->tune[0] = staged::SPLIT_MAX; s->tune[1] = staged::SPLIT_MIN_ITEMS;
+  s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
   s->variant = 1;
   const int rc = seeds_alloc(s);
   if(rc)
@@ -506,6 +510,12 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     }
     return 0;
   }
+  case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
+  case RMD_OPT_TUNE_SPARSE_MAX_SEEDS:
+    RMD_REQUIRE(value >= (option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS ? 0 : 1) && value <= 65535, "tuning value out of range");
+    RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 16, "RMD_OPT_TUNE_SPLIT_MAX: 1..16");
+    s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
+    return 0;
   case RMD_OPT_TEX_FRAC_BITS:
     RMD_REQUIRE(value >= 0 && value <= 12, "RMD_OPT_TEX_FRAC_BITS: 0..12");
     s->tex_frac_bits = value;
@@ -838,6 +848,10 @@ struct rmd_denoiser
   float *dense_out;
   float large_sigma_sq;
   uint64_t n_total;
+  // the iteration loop as a CUDA graph (launch-bound: ~3 us kernels), cached per (iterations, lambda)
+  cudaGraphExec_t loop_exec;
+  int loop_iterations;
+  float loop_lambda;
 };
 
 namespace
@@ -854,12 +868,44 @@ int denoiser_iterate(rmd_denoiser *d, float lambda, int iterations, int *final_b
   sp.theta = 0.5f;                      // :133
   sp.lambda = lambda;
   int cur = 0;
-  for(int i = 0; i < iterations; ++i)
+  const bool use_graph = iterations >= 8;
+  if(use_graph && !(d->loop_exec && d->loop_iterations == iterations && d->loop_lambda == lambda))
   {
-    sp.in = d->state[cur];
-    sp.out = d->state[cur ^ 1];
-    RMD_CUDA_TRY(launch_denoise_step(sp, d->stream));
-    cur ^= 1;
+    if(d->loop_exec) { cudaGraphExecDestroy(d->loop_exec); d->loop_exec = NULL; }
+    cudaGraph_t graph = NULL;
+    RMD_CUDA_TRY(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t err = cudaSuccess;
+    int c = 0;
+    for(int i = 0; i < iterations && err == cudaSuccess; ++i)
+    {
+      sp.in = d->state[c];
+      sp.out = d->state[c ^ 1];
+      err = launch_denoise_step(sp, d->stream);
+      c ^= 1;
+    }
+    const cudaError_t end_err = cudaStreamEndCapture(d->stream, &graph);
+    if(err != cudaSuccess) { if(graph) cudaGraphDestroy(graph); return fail_cuda(err, "denoise: capture"); }
+    RMD_CUDA_TRY(end_err);
+    err = cudaGraphInstantiate(&d->loop_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if(err != cudaSuccess) { d->loop_exec = NULL; return fail_cuda(err, "cudaGraphInstantiate"); }
+    d->loop_iterations = iterations;
+    d->loop_lambda = lambda;
+  }
+  if(use_graph)
+  {
+    RMD_CUDA_TRY(cudaGraphLaunch(d->loop_exec, d->stream));
+    cur = iterations & 1;
+  }
+  else
+  {
+    for(int i = 0; i < iterations; ++i)
+    {
+      sp.in = d->state[cur];
+      sp.out = d->state[cur ^ 1];
+      RMD_CUDA_TRY(launch_denoise_step(sp, d->stream));
+      cur ^= 1;
+    }
   }
   d->n_total += (uint64_t)(iterations > 0 ? iterations : 0);
   *final_buf = cur;
@@ -935,6 +981,7 @@ int rmd_denoiser_destroy(rmd_denoiser_t *d)
   DeviceGuard guard(d->device);
   cudaDeviceSynchronize();
   if(d->own_stream) cudaStreamDestroy(d->own_stream);
+  if(d->loop_exec) cudaGraphExecDestroy(d->loop_exec);
   cudaFree(d->state[0]); cudaFree(d->state[1]); cudaFree(d->gmu); cudaFree(d->dense_out);
   cudaGetLastError();
   delete d;

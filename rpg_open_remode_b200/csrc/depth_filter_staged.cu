@@ -58,6 +58,8 @@ struct __align__(128) StagedSmem
   int bbox[4];       // xmin, ymin, xmax, ymax over all segments of the CTA
   int strip_ox, strip_oy, strip_w, strip_rows;
   int is_last;
+  int items_acc;                       // work items of the tile (sum of the seeds' chunk counts)
+  unsigned int row_active[TILE_H];     // ballot of the seeds to update, per pixel row
   unsigned long long mbar;
 };
 
@@ -163,9 +165,9 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   {
     const int items_prev = P.tile_items_prev[tile];
     const unsigned int avg_per_slot = *P.frame_items_prev / (unsigned int)P.cta_slots;
-    if(items_prev > SPLIT_MIN_ITEMS && (unsigned int)items_prev > 2u * avg_per_slot)
+    if(items_prev > P.split_min_items && (unsigned int)items_prev > 2u * avg_per_slot)
       zeff = min((int)gridDim.z,
-                 (items_prev + SPLIT_ITEMS_PER_CTA - 1) / SPLIT_ITEMS_PER_CTA);
+                 (items_prev + P.split_items_per_cta - 1) / P.split_items_per_cta);
     if(z >= zeff)
       return;
   }
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   if(tid == 0)
   {
     S.bbox[0] = INT_MAX; S.bbox[1] = INT_MAX; S.bbox[2] = INT_MIN; S.bbox[3] = INT_MIN;
+    S.items_acc = 0;
     mbar_init(&S.mbar, 1);
   }
   const int n_active = __syncthreads_count(active);
@@ -256,27 +259,92 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   if(active)
   {
     seg = epipolar_segment(P, x, y, seed.x, seed.y);
-    // One pass over the seed's candidate positions, with the reference's own
-    // float accumulation of l (epipolar_match.cu:88): counts them, records l
-    // every 16th candidate (work items and the final match restart from
-    // there, bit-identically) and finds the contiguous range [k_lo, k_hi] that
-    // passes the image-bounds test (:91-97).  The segment is a straight line
-    // and the accepted region convex, so candidates outside the range can be
-    // skipped wholesale -- seeds whose projection left the image cost no items.
+    // The candidate positions follow the reference's own float accumulation of l
+    // (epipolar_match.cu:88).  One cheap pass counts them and records l every
+    // 16th candidate (work items and the final match restart from a checkpoint,
+    // bit-identically).  The candidates that pass the image-bounds test (:91-97)
+    // form one contiguous index range [k_lo, k_hi] -- the segment is a straight
+    // line, the accepted region convex and float rounding monotone -- so
+    // everything outside it is skipped wholesale and seeds whose projection left
+    // the image cost no work items.  The range is estimated in closed form and
+    // then fixed EXACTLY by testing the real candidates around the estimate.
     {
       int k = 0;
       for(float l = -seg.half_len; l <= seg.half_len; l += RMD_EPIPOLAR_STEP, ++k)
-      {
         if((k & (L_CHECKPOINT_STEP - 1)) == 0)
           S.l_checkpoint[pix][k / L_CHECKPOINT_STEP] = l;
+      n_cand = k;
+    }
+    if(n_cand > 0)
+    {
+      auto accepted = [&](int k) -> bool
+      {
+        float l = S.l_checkpoint[pix][k / L_CHECKPOINT_STEP];
+        for(int t = 0; t < (k & (L_CHECKPOINT_STEP - 1)); ++t) l += RMD_EPIPOLAR_STEP;
         const float2 px = make_float2(seg.mean.x + l * seg.dir.x, seg.mean.y + l * seg.dir.y);
-        if(!candidate_rejected<PS>(px, P.width, P.height))
+        return !candidate_rejected<PS>(px, P.width, P.height);
+      };
+      // l-interval in which P <= mean + l*dir < size - P holds, per axis
+      float la = -1.0e30f, lb = 1.0e30f;
+      bool none = false, exact_scan = false;
+      {
+        const float lo_x = (float)PS, hi_x = (float)(P.width - PS), lo_y = (float)PS, hi_y = (float)(P.height - PS);
+        const float m[2] = {seg.mean.x, seg.mean.y}, d[2] = {seg.dir.x, seg.dir.y};
+        const float lo[2] = {lo_x, lo_y}, hi[2] = {hi_x, hi_y};
+#pragma unroll
+        for(int ax = 0; ax < 2; ++ax)
         {
-          k_lo = min(k_lo, k);
-          k_hi = k;
+          if(!(fabsf(m[ax]) < 1.0e7f) || !(fabsf(d[ax]) <= 2.0f))
+            exact_scan = true;                       // NaN / inf: no shortcut
+          else if(fabsf(d[ax]) < 1.0e-6f)
+          {
+            // the segment does not move along this axis: inside, outside, or too close to call
+            if((fabsf(m[ax] - lo[ax]) <= 0.5f) || (fabsf(m[ax] - hi[ax]) <= 0.5f))
+              exact_scan = true;
+            else if((m[ax] < lo[ax]) || (m[ax] >= hi[ax]))
+              none = true;
+          }
+          else
+          {
+            const float t0 = (lo[ax] - m[ax]) / d[ax], t1 = (hi[ax] - m[ax]) / d[ax];
+            la = fmaxf(la, fminf(t0, t1));
+            lb = fminf(lb, fmaxf(t0, t1));
+          }
         }
       }
-      n_cand = k;
+      if(exact_scan)
+      {
+        for(int k = 0; k < n_cand; ++k)
+          if(accepted(k)) { k_lo = min(k_lo, k); k_hi = k; }
+      }
+      else if(!none)
+      {
+        // estimated index range, widened by 2 candidates on both sides
+        const float fa = (la + seg.half_len) / RMD_EPIPOLAR_STEP, fb = (lb + seg.half_len) / RMD_EPIPOLAR_STEP;
+        const int a = max(0, to_int_clamped(ceilf(fa)) - 2), b = min(n_cand - 1, to_int_clamped(floorf(fb)) + 2);
+        if(a <= b)
+        {
+          int first = -1, last = -1;
+          for(int k = a; k <= min(a + 4, b); ++k)
+            if(accepted(k)) { first = k; break; }
+          for(int k = b; k >= max(b - 4, a); --k)
+            if(accepted(k)) { last = k; break; }
+          if(first >= 0 && last >= 0)
+          {
+            // the estimate must have bracketed the true ends; if an end sits on
+            // the widened border (and is not the segment's end) scan further
+            while(first > 0 && first == a && accepted(first - 1)) { --first; }
+            while(last < n_cand - 1 && last == b && accepted(last + 1)) { ++last; }
+            k_lo = first; k_hi = last;
+          }
+          else if(b - a > 4)
+          {
+            // an end was not found next to its estimate: be exact over the whole window
+            for(int k = a; k <= b; ++k)
+              if(accepted(k)) { k_lo = min(k_lo, k); k_hi = k; }
+          }
+        }
+      }
     }
     const float ex0 = seg.mean.x - seg.half_len * seg.dir.x, ex1 = seg.mean.x + seg.half_len * seg.dir.x;
     const float ey0 = seg.mean.y - seg.half_len * seg.dir.y, ey1 = seg.mean.y + seg.half_len * seg.dir.y;
@@ -295,11 +363,21 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     SearchRec r;
     r.mean_x = seg.mean.x; r.mean_y = seg.mean.y; r.dir_x = seg.dir.x; r.dir_y = seg.dir.y;
     r.half_len = seg.half_len; r.sum_templ = stats.x; r.denom = stats.y;
-    r.n = (k_hi >= 0) ? (k_lo / CHUNK) : 0;  // first chunk with an accepted candidate
+    r.n = (k_hi >= 0) ? (k_lo | (k_hi << 8) | (1 << 16)) : 0;  // accepted candidate range, packed
     S.rec[pix] = r;
   }
   const unsigned long long kNoMatch = ((unsigned long long)orderable(-1.0f)) << 32;
   S.best[pix] = kNoMatch;
+  const int m_chunks = (k_hi >= 0) ? (k_hi / CHUNK - k_lo / CHUNK + 1) : 0;  // chunks with accepted candidates
+  {
+    const unsigned int act = __ballot_sync(0xffffffffu, active);
+    const int m_row = __reduce_add_sync(0xffffffffu, m_chunks);
+    if(lane == 0)
+    {
+      S.row_active[wid] = act;
+      if(m_row) atomicAdd(&S.items_acc, m_row);
+    }
+  }
   bx_lo = __reduce_min_sync(0xffffffffu, bx_lo); by_lo = __reduce_min_sync(0xffffffffu, by_lo);
   bx_hi = __reduce_max_sync(0xffffffffu, bx_hi); by_hi = __reduce_max_sync(0xffffffffu, by_hi);
   if(lane == 0 && bx_lo <= bx_hi)
@@ -310,6 +388,83 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   __syncthreads();
 
   RMD_STAMP(2);
+  if(lead && tid == 0)
+  {
+    if(gridDim.z > 1)
+    {
+      P.tile_items_next[tile] = S.items_acc;
+      atomicAdd(P.frame_items_next, (unsigned int)S.items_acc);
+    }
+    if(stamps) stamps[7] = S.items_acc;
+  }
+
+  // ---- sparse tile (the common case once most seeds have converged): a handful
+  // of seeds does not pay for a TMA round trip and a CTA-wide work list.  One
+  // warp per seed, lanes = candidates, taps straight from global memory (L2),
+  // arg-max with warp shuffles on the same (ncc, -index) key.
+  const bool sparse = (n_active <= P.sparse_max_seeds) && (zeff == 1);
+  if(sparse)
+  {
+    int seen = 0;
+    for(int r = 0; r < TILE_H; ++r)
+    {
+      unsigned int mask = S.row_active[r];
+      while(mask)
+      {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if((seen++ % NWARPS) != wid)
+          continue;
+        const SearchRec R = S.rec[r * TILE_W + src];
+        unsigned long long key = kNoMatch;
+        if(R.n >> 16)
+        {
+          const int ka = R.n & 0xff, kb = (R.n >> 8) & 0xff;
+          float templ[PS * PS];
+#pragma unroll
+          for(int j = 0; j < PS; ++j)
+#pragma unroll
+            for(int i = 0; i < PS; ++i)
+              templ[j * PS + i] = __ldg(P.ref + (size_t)(y0 + r - PS / 2 + j) * P.ref_stride + (x0 + src - PS / 2 + i));
+          float best_ncc = -1.0f;
+          int best_idx = 0;
+#pragma unroll 1
+          for(int k = ka + lane; k <= kb; k += 32)
+          {
+            float l = S.l_checkpoint[r * TILE_W + src][k / L_CHECKPOINT_STEP];
+            for(int t = 0; t < (k & (L_CHECKPOINT_STEP - 1)); ++t) l += RMD_EPIPOLAR_STEP;
+            const float2 px = make_float2(R.mean_x + l * R.dir_x, R.mean_y + l * R.dir_y);
+            if(candidate_rejected<PS>(px, P.width, P.height))
+              continue;
+            const TapFrame frame = tap_frame<PS>(px, P.tex_quant);
+            const GlobalTaps taps(P.curr, P.curr_stride, frame);
+            const float ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+            if(ncc > best_ncc)
+            {
+              best_ncc = ncc;
+              best_idx = k;
+            }
+          }
+          if(best_ncc > -1.0f)
+            key = (((unsigned long long)orderable(best_ncc)) << 32) |
+                  (unsigned long long)(0xffffffffu - (unsigned int)best_idx);
+        }
+#pragma unroll
+        for(int off = 16; off > 0; off >>= 1)
+        {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, off);
+          key = (other > key) ? other : key;
+        }
+        if(lane == 0)
+          S.best[r * TILE_W + src] = key;
+      }
+    }
+    __syncthreads();
+    RMD_STAMP(3);
+    RMD_STAMP(4);
+  }
+  else
+  {
   // ---- 2. TMA: reference tile and current-image strip -> shared memory
   if(tid == 0)
   {
@@ -346,7 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   {
     // level c of a row = the seeds that still have a c-th chunk of candidates;
     // ballots are warp-uniform, so every lane tracks the running item count
-    const int m = (k_hi >= 0) ? (k_hi / CHUNK - k_lo / CHUNK + 1) : 0;  // chunks with accepted candidates
+    const int m = m_chunks;
     int cum = 0;
     for(int c = 0; c < MAX_CHUNKS; ++c)
     {
@@ -365,18 +520,6 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     }
   }
   __syncthreads();  // publishes the work lists and the strip geometry (built while the TMA is in flight)
-  if(lead && tid == 0 && (gridDim.z > 1 || stamps))
-  {
-    int items = 0;
-#pragma unroll
-    for(int k = 0; k < TILE_H; ++k) items += S.level_total[k];
-    if(gridDim.z > 1)
-    {
-      P.tile_items_next[tile] = items;
-      atomicAdd(P.frame_items_next, (unsigned int)items);
-    }
-    if(stamps) stamps[7] = items;
-  }
   const int strip_ox = S.strip_ox, strip_oy = S.strip_oy, strip_w = S.strip_w, strip_rows = S.strip_rows;
   mbar_wait(&S.mbar, 0);
   RMD_STAMP(3);
@@ -417,7 +560,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
 
       // l of the chunk's first candidate: the same float accumulation as the
       // reference's loop (epipolar_match.cu:88), so positions are bit-identical
-      const int first = (R.n + c) * CHUNK;
+      const int first = ((R.n & 0xff) / CHUNK + c) * CHUNK;
       float l = S.l_checkpoint[r * TILE_W + src][first / L_CHECKPOINT_STEP];
       for(int k = 0; k < (first & (L_CHECKPOINT_STEP - 1)); ++k) l += RMD_EPIPOLAR_STEP;
 
@@ -460,6 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   }
   __syncthreads();
   RMD_STAMP(4);
+  }  // staged (non-sparse) path
 
   // ---- 3b. a split tile: merge the partial arg-max of its CTAs in global
   // memory; the last CTA to arrive finalises the tile (and leaves the keys and

@@ -103,6 +103,7 @@ struct FilterParams
   long long *timeline;           // debug: 8 clock64() stamps per CTA of the staged kernel, or null
   // staged kernel, busy-tile splitting (depth_filter_staged.cu)
   int split_max;                         // grid.z; 1 = never split
+  int split_min_items, split_items_per_cta, sparse_max_seeds;  // tuning (staged_maps.cuh defaults)
   int cta_slots;                         // resident CTAs of the whole GPU (SMs x CTAs per SM)
   unsigned long long *tile_keys;         // [tiles][256] partial arg-max keys of split tiles
   unsigned int *tile_arrivals;           // [tiles] CTAs of a split tile that finished searching

@@ -43,6 +43,10 @@ for k in range(1, 131):
                 busy[smid] = (end[sel].max() - start[sel].min()) / 1e3
             b = np.array(list(busy.values()))
             print(f"   per-SM first-start..last-end us: min {b.min():.1f} median {np.median(b):.1f} max {b.max():.1f}; CTAs/SM {len(t)/len(b):.1f}")
+            order = np.argsort(-(t[:, 5] - t[:, 0]))[:8]
+            for i in order:
+                print(f"   slow CTA tile {i:4d} (x {i % 20:2d}, y {i // 20:2d}) sm {t[i,6]:3d}: total {(t[i,5]-t[i,0])/1e3:6.1f} us; "
+                      f"classify {t[i,1]:6d} setup {t[i,2]-t[i,1]:6d} tma {t[i,3]-t[i,2]:6d} search {t[i,4]-t[i,3]:6d} cycles; items {t[i,7]}")
             inact = ~act
             if inact.any():
                 di = (t[:, 5] - t[:, 0])[inact] if False else None

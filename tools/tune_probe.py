@@ -1,0 +1,40 @@
+"""Sensitivity of the VGA 200-frame sequence time to the staged kernel's tuning knobs (GPU box)."""
+import os, sys, itertools, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import rpg_open_remode_b200 as rmd
+from rpg_open_remode_b200 import synth
+
+W, H, N = 640, 480, 200
+seq = synth.SyntheticSequence(W, H, seed=0x5EED0002)
+frames = np.empty((N, H, W), np.float32); poses = np.empty((N, 12), np.float32)
+for k in range(N):
+    f = seq.frame(k, want_depth=(k == 0)); frames[k] = f.image; poses[k] = f.T_cam_world.reshape(12)
+    if k == 0: dmin, dmax = float(f.depth.min()), float(f.depth.max())
+dev = torch.device("cuda", 0); stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+d_frames = torch.from_numpy(frames).to(dev)
+g = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera)); g.setStream(stream.cuda_stream); g.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED)
+
+def run(cfg):
+    for opt, val in zip((10, 11, 12, 13), cfg): g.setOption(opt, val)
+    best = 1e9; seg = None
+    for rep in range(4):
+        g.setReferenceImageDevice(d_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(stream)
+        g.updateDeviceBatch(d_frames[1].data_ptr(), W * H * 4, W * 4, poses[1:20]); ev[1].record(stream)
+        g.updateDeviceBatch(d_frames[20].data_ptr(), W * H * 4, W * 4, poses[20:100]); ev[2].record(stream)
+        g.updateDeviceBatch(d_frames[100].data_ptr(), W * H * 4, W * 4, poses[100:]); ev[3].record(stream)
+        torch.cuda.synchronize()
+        tot = ev[0].elapsed_time(ev[3])
+        if tot < best:
+            best = tot; seg = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+    return best, seg
+
+for cfg in [(8, 192, 128, 16), (1, 192, 128, 16), (4, 192, 128, 16), (8, 192, 128, 0), (8, 192, 128, 64), (8, 64, 64, 16),
+            (8, 512, 256, 16), (16, 192, 128, 16), (8, 192, 128, 256)]:
+    tot, seg = run(cfg)
+    print("split_max %2d min_items %4d per_cta %4d sparse %3d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-199 %.2f ms" %
+          (*cfg, tot, 199 / tot * 1e3, *seg))
