@@ -1,27 +1,32 @@
 // depth_filter_staged.cu -- fused depth filter, staged variant for sm_100a.
 //
-// One CTA = 32x2 pixels of the reference view (one warp per row; small CTAs so
-// that clusters of unconverged seeds spread over all SMs).  Per frame:
+// One CTA (8 warps) per 32x8 tile of the reference view, one warp per pixel
+// row.  Per frame (details and measurements: DESIGN.md section 4.1):
 //   0. classify every seed (convergence check, src/seed_check.cu:29-67);
-//      CTAs without a seed left to update stop here after 4 B/pixel;
+//      absorbing seeds cost 4 bytes, a tile with nothing to update ends here;
 //   1. every active seed projects its depth interval into the current frame
-//      (src/epipolar_match.cu:60-75) and the CTA reduces the bounding box of
-//      all its search segments;
-//   2. one thread issues TMA loads (cp.async.bulk.tensor.2d, mbarrier
-//      complete_tx) of the reference tile (+halo) and of that strip of the
-//      current frame into shared memory;
-//   3. each warp flattens the (seed, 8-candidate chunk) pairs of its 32 seeds
-//      into a chunk-major work list and hands items to lanes round-robin, so
-//      lanes stay busy whatever the mix of search lengths; the NCC of a
-//      candidate is evaluated by the same code as in the direct variant
-//      (depth_filter_math.cuh) on taps read from the shared-memory strip
-//      (from global memory for the rare block outside it); per-seed arg-max
-//      is combined with a shared-memory 64-bit atomicMax on (ncc, -index),
-//      which reproduces the reference's "first maximum wins" order
-//      (epipolar_match.cu:125-129);
+//      (src/epipolar_match.cu:60-75), counts its candidates with the
+//      reference's own float accumulation (checkpointing l every 16th), finds
+//      the exact contiguous range of candidates inside the image, and the CTA
+//      reduces the bounding box of all search segments;
+//   2. one thread issues TMA loads (cp.async.bulk.tensor.2d -> UTMALDG,
+//      mbarrier complete_tx) of the reference tile (+halo) and of the strip of
+//      the current frame under that bounding box into shared memory;
+//   3. the seeds' candidates are cut into 4-candidate chunks; per pixel row they
+//      form a chunk-major work list and all warps take 32-item rounds of the 8
+//      lists round-robin, so lanes stay busy whatever the mix of search
+//      lengths; a candidate's NCC is evaluated by the same code as in the direct
+//      variant (depth_filter_math.cuh) on taps from the shared-memory strip
+//      (from global memory for the rare block outside it); per-seed arg-max is a
+//      shared-memory 64-bit atomicMax on (ncc, -index), which reproduces the
+//      reference's "first maximum wins" (epipolar_match.cu:125-129);
+//   3b. a tile that was much busier than average in the previous frame is
+//      shared by up to 8 CTAs (blockIdx.z), merged through global atomics;
+//   3c. a tile with at most 16 seeds to update skips staging: one warp per seed,
+//      lanes = candidates, warp-shuffle arg-max;
 //   4. the owner thread triangulates the best match and updates its seed
 //      (src/seed_update.cu:40-121) in registers and writes it back once.
-// Results are bit-identical to the direct variant.
+// Results are bit-identical to the direct variant (tests/test_gpu_configs.py).
 #include <cudaTypedefs.h>
 
 #include <limits.h>
