@@ -130,7 +130,10 @@ struct rmd_seeds
   int n_tiles, cta_slots;
   unsigned long long *tile_keys;
   unsigned int *tile_arrivals;
-  int *tile_items[2];
+  int *tile_zeff[2];
+  unsigned int *helper_list[2];
+  unsigned int *helper_count;  // 3 rotating slots
+  int tiles_x;
   unsigned int *frame_items;   // 3 rotating slots
   int tune[4];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
@@ -168,8 +171,13 @@ int seeds_alloc(rmd_seeds *s)
     s->cta_slots = sms * 3;
     RMD_CUDA_TRY(cudaMalloc(&s->tile_keys, sizeof(unsigned long long) * (size_t)s->n_tiles * staged::NPIX));
     RMD_CUDA_TRY(cudaMalloc(&s->tile_arrivals, sizeof(unsigned int) * (size_t)s->n_tiles));
-    RMD_CUDA_TRY(cudaMalloc(&s->tile_items[0], sizeof(int) * (size_t)s->n_tiles));
-    RMD_CUDA_TRY(cudaMalloc(&s->tile_items[1], sizeof(int) * (size_t)s->n_tiles));
+    s->tiles_x = (w + staged::TILE_W - 1) / staged::TILE_W;
+    for(int i = 0; i < 2; ++i)
+    {
+      RMD_CUDA_TRY(cudaMalloc(&s->tile_zeff[i], sizeof(int) * (size_t)s->n_tiles));
+      RMD_CUDA_TRY(cudaMalloc(&s->helper_list[i], sizeof(unsigned int) * staged::HELPER_CAP));
+    }
+    RMD_CUDA_TRY(cudaMalloc(&s->helper_count, 3 * sizeof(unsigned int)));
     RMD_CUDA_TRY(cudaMalloc(&s->frame_items, 3 * sizeof(unsigned int)));
   }
   RMD_CUDA_TRY(cudaEventCreate(&s->t0));
@@ -196,7 +204,8 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->dense_tmp);
   cudaFree(s->counters);
   cudaFree(s->timeline);
-  cudaFree(s->tile_keys); cudaFree(s->tile_arrivals); cudaFree(s->tile_items[0]); cudaFree(s->tile_items[1]);
+  cudaFree(s->tile_keys); cudaFree(s->tile_arrivals); cudaFree(s->tile_zeff[0]); cudaFree(s->tile_zeff[1]);
+  cudaFree(s->helper_list[0]); cudaFree(s->helper_list[1]); cudaFree(s->helper_count);
   cudaFree(s->frame_items);
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
@@ -247,8 +256,9 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   RMD_CUDA_TRY(launch_seed_init(ip, s->patch, s->stream));
   RMD_CUDA_TRY(cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned int), s->stream));
   // no tile is split in the first frame of a keyframe; keys hold "no match"
-  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_items[0], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_items[1], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_zeff[0], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_zeff[1], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->helper_count, 0, 3 * sizeof(unsigned int), s->stream));
   RMD_CUDA_TRY(cudaMemsetAsync(s->frame_items, 0, 3 * sizeof(unsigned int), s->stream));
   RMD_CUDA_TRY(cudaMemsetAsync(s->tile_arrivals, 0, sizeof(unsigned int) * (size_t)s->n_tiles, s->stream));
   RMD_CUDA_TRY(launch_fill_u64(s->tile_keys, (size_t)s->n_tiles * staged::NPIX, 0x407FFFFF00000000ull, s->stream));
@@ -301,8 +311,14 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.cta_slots = s->cta_slots;
     P.tile_keys = s->tile_keys;
     P.tile_arrivals = s->tile_arrivals;
-    P.tile_items_prev = s->tile_items[(f + 1) & 1];
-    P.tile_items_next = s->tile_items[f & 1];
+    P.n_tiles = s->n_tiles; P.tiles_x = s->tiles_x; P.helper_cap = staged::HELPER_CAP;
+    P.tile_zeff_cur = s->tile_zeff[(f + 1) & 1];
+    P.tile_zeff_next = s->tile_zeff[f & 1];
+    P.helper_list_cur = s->helper_list[(f + 1) & 1];
+    P.helper_list_next = s->helper_list[f & 1];
+    P.helper_count_cur = s->helper_count + ((f + 2) % 3);
+    P.helper_count_next = s->helper_count + (f % 3);
+    P.helper_count_zero = s->helper_count + ((f + 1) % 3);
     P.frame_items_prev = s->frame_items + ((f + 2) % 3);
     P.frame_items_next = s->frame_items + (f % 3);
     P.frame_items_zero = s->frame_items + ((f + 1) % 3);

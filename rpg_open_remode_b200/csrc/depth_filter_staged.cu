@@ -21,7 +21,8 @@
 //      shared-memory 64-bit atomicMax on (ncc, -index), which reproduces the
 //      reference's "first maximum wins" (epipolar_match.cu:125-129);
 //   3b. a tile that was much busier than average in the previous frame is
-//      shared by up to 8 CTAs (blockIdx.z), merged through global atomics;
+//      shared by up to 8 CTAs (helper CTAs listed by the previous frame), merged
+//      through global atomics;
 //   3c. a tile with at most 16 seeds to update skips staging: one warp per seed,
 //      lanes = candidates, warp-shuffle arg-max;
 //   4. the owner thread triangulates the best match and updates its seed
@@ -154,34 +155,39 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   const int lane = threadIdx.x, wid = threadIdx.y;   // warp `wid` owns pixel row `wid` of the tile
   const int tid = wid * TILE_W + lane;
   const int pix = tid;
-  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
-  const int x = x0 + lane, y = y0 + wid;
-  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-  const int z = blockIdx.z;
-
-  // ---- split factor of this tile.  A frame's duration is bounded below by its
-  // busiest tile (up to 9216 work items on one CTA) once most seeds have
-  // converged; tiles that were much busier than the per-slot average in the
-  // PREVIOUS frame are processed by zeff CTAs (blockIdx.z < zeff), each taking
-  // every zeff-th round of the work list.  All CTAs of a tile read the same
-  // two numbers, so they agree on zeff without talking to each other.
-  int zeff = 1;
-  if(gridDim.z > 1)
+  // ---- which tile, and which share of it.  A frame's duration is bounded below
+  // by its busiest tile (up to 9216 work items on one CTA) once most seeds have
+  // converged, so a tile that was much busier than the per-slot average in the
+  // PREVIOUS frame is processed by zeff CTAs, each taking every zeff-th round
+  // of its work list.  CTAs [0, n_tiles) are the tiles' lead CTAs; CTAs beyond
+  // are helpers that look up their (tile, share, zeff) in a list the lead CTAs
+  // wrote during the previous frame -- no empty grid layers to dispatch.
+  int tile, z, zeff;
+  if((int)blockIdx.x < P.n_tiles)
   {
-    const int items_prev = P.tile_items_prev[tile];
-    const unsigned int avg_per_slot = *P.frame_items_prev / (unsigned int)P.cta_slots;
-    if(items_prev > P.split_min_items && (unsigned int)items_prev > 2u * avg_per_slot)
-      zeff = min((int)gridDim.z,
-                 (items_prev + P.split_items_per_cta - 1) / P.split_items_per_cta);
-    if(z >= zeff)
-      return;
+    tile = (int)blockIdx.x;
+    z = 0;
+    zeff = (P.split_max > 1) ? max(1, P.tile_zeff_cur[tile]) : 1;
   }
+  else
+  {
+    const int h = (int)blockIdx.x - P.n_tiles;
+    if(h >= min((int)*P.helper_count_cur, P.helper_cap))
+      return;
+    const unsigned int e = P.helper_list_cur[h];
+    tile = (int)(e & 0xfffffu);
+    z = (int)((e >> 20) & 0x3fu);
+    zeff = (int)(e >> 26);
+  }
+  const int x0 = (tile % P.tiles_x) * TILE_W, y0 = (tile / P.tiles_x) * TILE_H;
+  const int x = x0 + lane, y = y0 + wid;
   const bool lead = (z == 0);  // the CTA that records what all of them compute identically
 
-  if(tile == 0 && lead && tid == 0)
+  if(blockIdx.x == 0 && tid == 0)
   {
     *P.converged_next = 0u;
     *P.frame_items_zero = 0u;
+    *P.helper_count_zero = 0u;
   }
 
   // debug timeline (RMD_OPT_DEBUG_TIMELINE), lead CTA only:
@@ -249,8 +255,8 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   const int n_active = __syncthreads_count(active);
   if(n_active == 0)
   {
-    if(lead && tid == 0 && gridDim.z > 1)
-      P.tile_items_next[tile] = 0;
+    if(lead && tid == 0 && P.split_max > 1)
+      P.tile_zeff_next[tile] = 1;
     if(stamps && tid == 0) stamps[1] = -(clock64() - stamp_t0);
     return;
   }
@@ -395,10 +401,23 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   RMD_STAMP(2);
   if(lead && tid == 0)
   {
-    if(gridDim.z > 1)
+    if(P.split_max > 1)
     {
-      P.tile_items_next[tile] = S.items_acc;
-      atomicAdd(P.frame_items_next, (unsigned int)S.items_acc);
+      // this tile's share count for the NEXT frame, and its helper CTAs
+      const int items = S.items_acc;
+      atomicAdd(P.frame_items_next, (unsigned int)items);
+      const unsigned int avg_per_slot = *P.frame_items_prev / (unsigned int)P.cta_slots;
+      int znext = 1;
+      if(items > P.split_min_items && (unsigned int)items > 2u * avg_per_slot)
+        znext = min(P.split_max, (items + P.split_items_per_cta - 1) / P.split_items_per_cta);
+      if(znext > 1)
+      {
+        const int base = (int)atomicAdd(P.helper_count_next, (unsigned int)(znext - 1));
+        znext = 1 + max(0, min(znext - 1, P.helper_cap - base));   // what fits in the list
+        for(int k = 1; k < znext; ++k)
+          P.helper_list_next[base + k - 1] = (unsigned int)tile | ((unsigned int)k << 20) | ((unsigned int)znext << 26);
+      }
+      P.tile_zeff_next[tile] = znext;
     }
     if(stamps) stamps[7] = S.items_acc;
   }
@@ -765,8 +784,7 @@ static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, 
     if(device >= 0 && device < 64) configured[device] = true;
   }
   const dim3 block(TILE_W, NWARPS);
-  const dim3 grid((P.width + TILE_W - 1) / TILE_W, (P.height + TILE_H - 1) / TILE_H,
-                  P.split_max > 1 ? P.split_max : 1);
+  const dim3 grid(P.n_tiles + (P.split_max > 1 ? P.helper_cap : 0));
   depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);  // grid.z = P.split_max
   return cudaGetLastError();
 }

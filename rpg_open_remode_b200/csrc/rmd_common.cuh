@@ -107,8 +107,14 @@ struct FilterParams
   int cta_slots;                         // resident CTAs of the whole GPU (SMs x CTAs per SM)
   unsigned long long *tile_keys;         // [tiles][256] partial arg-max keys of split tiles
   unsigned int *tile_arrivals;           // [tiles] CTAs of a split tile that finished searching
-  const int *tile_items_prev;            // [tiles] work items of each tile in the previous frame
-  int *tile_items_next;                  // [tiles] ... written this frame
+  int n_tiles, tiles_x;                  // tile grid of the image
+  const int *tile_zeff_cur;              // [tiles] CTAs sharing each tile in this frame (0/1 = one)
+  int *tile_zeff_next;                   // [tiles] ... decided now for the next frame
+  const unsigned int *helper_list_cur;   // helper CTAs of this frame: tile | share << 20 | zeff << 26
+  unsigned int *helper_list_next;
+  const unsigned int *helper_count_cur;  // entries of helper_list_cur
+  unsigned int *helper_count_next, *helper_count_zero;
+  int helper_cap;                        // capacity of the helper lists = helper CTAs launched
   const unsigned int *frame_items_prev;  // work items of the whole previous frame
   unsigned int *frame_items_next;        // ... accumulated this frame
   unsigned int *frame_items_zero;        // slot to clear for the next frame
