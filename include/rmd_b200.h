@@ -95,7 +95,8 @@ enum rmd_seeds_option {
   RMD_OPT_TUNE_SPLIT_MAX = 10,
   RMD_OPT_TUNE_SPLIT_MIN_ITEMS = 11,
   RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA = 12,
-  RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13
+  RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13,
+  RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

@@ -104,7 +104,7 @@ struct rmd_seeds
   float2 *matches; size_t matches_pitch;
   float *planar[6]; size_t planar_pitch;   // mu, sigma_sq, a, b, sum_templ, denom
   float *dense_tmp;                        // width*height floats, uploads/downloads
-  unsigned int *counters;                  // 2 x converged count
+  unsigned int *counters;                  // 2 x converged count (ping-pong) + converged seeds of retired tiles
 
   // scene / algorithm parameters (src/seed_matrix.cu:96-104)
   float min_depth, max_depth, avg_depth, depth_range, sigma_sq_max;
@@ -130,12 +130,12 @@ struct rmd_seeds
   int n_tiles, cta_slots;
   unsigned long long *tile_keys;
   unsigned int *tile_arrivals;
-  int *tile_zeff[2];
-  unsigned int *helper_list[2];
-  unsigned int *helper_count;  // 3 rotating slots
+  unsigned int *heavy_list[2], *light_list[2];  // work lists: this frame's / the next frame's
+  unsigned int *work_counts;   // 3 rotating slots of {heavy, light, helpers, items}
+  bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
+  bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  unsigned int *frame_items;   // 3 rotating slots
-  int tune[4];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds
+  int tune[5];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
 };
 
@@ -161,8 +161,8 @@ int seeds_alloc(rmd_seeds *s)
     RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
     RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
   }
-  RMD_CUDA_TRY(cudaMalloc(&s->counters, 2 * sizeof(unsigned int)));
-  RMD_CUDA_TRY(cudaMemset(s->counters, 0, 2 * sizeof(unsigned int)));
+  RMD_CUDA_TRY(cudaMalloc(&s->counters, 3 * sizeof(unsigned int)));
+  RMD_CUDA_TRY(cudaMemset(s->counters, 0, 3 * sizeof(unsigned int)));
   RMD_CUDA_TRY(cudaMemset2D(s->conv, s->conv_pitch, 0, sizeof(int) * (size_t)w, h));
   {
     s->n_tiles = ((w + staged::TILE_W - 1) / staged::TILE_W) * ((h + staged::TILE_H - 1) / staged::TILE_H);
@@ -174,11 +174,10 @@ int seeds_alloc(rmd_seeds *s)
     s->tiles_x = (w + staged::TILE_W - 1) / staged::TILE_W;
     for(int i = 0; i < 2; ++i)
     {
-      RMD_CUDA_TRY(cudaMalloc(&s->tile_zeff[i], sizeof(int) * (size_t)s->n_tiles));
-      RMD_CUDA_TRY(cudaMalloc(&s->helper_list[i], sizeof(unsigned int) * staged::HELPER_CAP));
+      RMD_CUDA_TRY(cudaMalloc(&s->heavy_list[i], sizeof(unsigned int) * (size_t)(s->n_tiles + staged::HELPER_CAP)));
+      RMD_CUDA_TRY(cudaMalloc(&s->light_list[i], sizeof(unsigned int) * (size_t)s->n_tiles));
     }
-    RMD_CUDA_TRY(cudaMalloc(&s->helper_count, 3 * sizeof(unsigned int)));
-    RMD_CUDA_TRY(cudaMalloc(&s->frame_items, 3 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMalloc(&s->work_counts, 12 * sizeof(unsigned int)));
   }
   RMD_CUDA_TRY(cudaEventCreate(&s->t0));
   RMD_CUDA_TRY(cudaEventCreate(&s->t1));
@@ -204,9 +203,9 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->dense_tmp);
   cudaFree(s->counters);
   cudaFree(s->timeline);
-  cudaFree(s->tile_keys); cudaFree(s->tile_arrivals); cudaFree(s->tile_zeff[0]); cudaFree(s->tile_zeff[1]);
-  cudaFree(s->helper_list[0]); cudaFree(s->helper_list[1]); cudaFree(s->helper_count);
-  cudaFree(s->frame_items);
+  cudaFree(s->tile_keys); cudaFree(s->tile_arrivals);
+  cudaFree(s->heavy_list[0]); cudaFree(s->heavy_list[1]); cudaFree(s->light_list[0]); cudaFree(s->light_list[1]);
+  cudaFree(s->work_counts);
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
@@ -254,12 +253,9 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   ip.conv = s->conv; ip.conv_stride = (int)(s->conv_pitch / sizeof(int));
   ip.avg_depth = s->avg_depth; ip.sigma_sq_max = s->sigma_sq_max;
   RMD_CUDA_TRY(launch_seed_init(ip, s->patch, s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->counters, 0, 2 * sizeof(unsigned int), s->stream));
-  // no tile is split in the first frame of a keyframe; keys hold "no match"
-  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_zeff[0], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->tile_zeff[1], 0, sizeof(int) * (size_t)s->n_tiles, s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->helper_count, 0, 3 * sizeof(unsigned int), s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->frame_items, 0, 3 * sizeof(unsigned int), s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->counters, 0, 3 * sizeof(unsigned int), s->stream));
+  // the first staged frame of a keyframe starts from the full work list; keys hold "no match"
+  s->worklist_valid = false;
   RMD_CUDA_TRY(cudaMemsetAsync(s->tile_arrivals, 0, sizeof(unsigned int) * (size_t)s->n_tiles, s->stream));
   RMD_CUDA_TRY(launch_fill_u64(s->tile_keys, (size_t)s->n_tiles * staged::NPIX, 0x407FFFFF00000000ull, s->stream));
   s->n_total += 1;
@@ -312,16 +308,13 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.tile_keys = s->tile_keys;
     P.tile_arrivals = s->tile_arrivals;
     P.n_tiles = s->n_tiles; P.tiles_x = s->tiles_x; P.helper_cap = staged::HELPER_CAP;
-    P.tile_zeff_cur = s->tile_zeff[(f + 1) & 1];
-    P.tile_zeff_next = s->tile_zeff[f & 1];
-    P.helper_list_cur = s->helper_list[(f + 1) & 1];
-    P.helper_list_next = s->helper_list[f & 1];
-    P.helper_count_cur = s->helper_count + ((f + 2) % 3);
-    P.helper_count_next = s->helper_count + (f % 3);
-    P.helper_count_zero = s->helper_count + ((f + 1) % 3);
-    P.frame_items_prev = s->frame_items + ((f + 2) % 3);
-    P.frame_items_next = s->frame_items + (f % 3);
-    P.frame_items_zero = s->frame_items + ((f + 1) % 3);
+    P.heavy_min_items = s->tune[4];
+    P.heavy_cur = s->heavy_list[(f + 1) & 1]; P.heavy_next = s->heavy_list[f & 1];
+    P.light_cur = s->light_list[(f + 1) & 1]; P.light_next = s->light_list[f & 1];
+    P.counts_cur = s->work_counts + 4 * ((f + 2) % 3);
+    P.counts_next = s->work_counts + 4 * (f % 3);
+    P.counts_zero = s->work_counts + 4 * ((f + 1) % 3);
+    P.retired_converged = s->counters + 2;
   }
 
   if(s->timing) RMD_CUDA_TRY(cudaEventRecord(s->t0, s->stream));
@@ -330,11 +323,25 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     if(!s->maps) s->maps = new StagedMaps();
     const int rc = s->maps->encode(P, s->patch);
     if(rc) return rc;
+    if(!s->worklist_valid)
+    {
+      // every tile once, in image order, no helpers; nothing retired yet
+      RMD_CUDA_TRY(cudaMemsetAsync(s->work_counts, 0, 12 * sizeof(unsigned int), s->stream));
+      RMD_CUDA_TRY(cudaMemsetAsync(s->counters + 2, 0, sizeof(unsigned int), s->stream));
+      RMD_CUDA_TRY(launch_worklist_init(const_cast<unsigned int*>(P.light_cur),
+                                        const_cast<unsigned int*>(P.counts_cur), s->n_tiles, s->stream));
+      s->worklist_valid = true;
+    }
+    if(s->timeline)
+      RMD_CUDA_TRY(cudaMemsetAsync(s->timeline, 0, s->timeline_bytes, s->stream));
+    s->last_staged = true;
     RMD_CUDA_TRY(launch_depth_filter_staged(P, *s->maps, s->patch, s->stream));
   }
   else
   {
     RMD_CUDA_TRY(launch_depth_filter_direct(P, s->patch, s->stream));
+    s->worklist_valid = false;   // the direct kernel does not maintain the staged kernel's work list
+    s->last_staged = false;
   }
   if(s->timing)
   {
@@ -462,6 +469,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tex_frac_bits = 8;
   s->tune[0] = staged::SPLIT_MAX; s->tune[1] = staged::SPLIT_MIN_ITEMS;
   s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
+  s->tune[4] = staged::HEAVY_MIN_ITEMS;
   s->variant = 1;
   const int rc = seeds_alloc(s);
   if(rc)
@@ -527,7 +535,7 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     return 0;
   }
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
-  case RMD_OPT_TUNE_SPARSE_MAX_SEEDS:
+  case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS:
     RMD_REQUIRE(value >= (option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS ? 0 : 1) && value <= 65535, "tuning value out of range");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 16, "RMD_OPT_TUNE_SPLIT_MAX: 1..16");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
@@ -727,6 +735,7 @@ int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
   }
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   s->trust_conv = false;  // the map may no longer agree with the parameters
+  s->worklist_valid = false;
   return 0;
 }
 
@@ -796,14 +805,14 @@ int rmd_seeds_converged_count(rmd_seeds_t *s, size_t *count)
 {
   RMD_REQUIRE(s && count, "rmd_seeds_converged_count: null argument");
   DeviceGuard guard(s->device);
-  unsigned int v = 0;
+  unsigned int v[3] = {0u, 0u, 0u};
   if(s->frame_index > 0)
   {
-    RMD_CUDA_TRY(cudaMemcpyAsync(&v, s->counters + (s->frame_index & 1), sizeof(v),
-                                 cudaMemcpyDeviceToHost, s->stream));
+    RMD_CUDA_TRY(cudaMemcpyAsync(v, s->counters, sizeof(v), cudaMemcpyDeviceToHost, s->stream));
     RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   }
-  *count = v;
+  // seeds of tiles the staged kernel has retired from its work list are counted in v[2]
+  *count = (size_t)v[s->frame_index & 1] + (s->last_staged ? (size_t)v[2] : 0);
   return 0;
 }
 

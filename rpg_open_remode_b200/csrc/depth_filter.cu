@@ -220,6 +220,24 @@ cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long lon
   return cudaGetLastError();
 }
 
+// Work list of the staged kernel's first frame: every tile once, image order.
+__global__ void worklist_init_kernel(unsigned int *light, unsigned int *counts, int n_tiles)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n_tiles)
+    light[i] = (unsigned int)i | (1u << 26);   // share 0 of 1
+  if(i == 0)
+  {
+    counts[0] = 0u; counts[1] = (unsigned int)n_tiles; counts[2] = 0u; counts[3] = 0u;
+  }
+}
+
+cudaError_t launch_worklist_init(unsigned int *light, unsigned int *counts, int n_tiles, cudaStream_t stream)
+{
+  worklist_init_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(light, counts, n_tiles);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_u8_to_float(const uint8_t *src, int src_stride, float *dst, int dst_stride,
                                int width, int height, cudaStream_t stream)
 {

@@ -34,6 +34,9 @@ cudaError_t launch_depth_filter_staged(const FilterParams &P, const StagedMaps &
 // dst[i] = value for i < n (64-bit pattern fill)
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);
 
+// light[i] = tile i (share 0 of 1) for i < n_tiles; counts = {0, n_tiles, 0, 0}
+cudaError_t launch_worklist_init(unsigned int *light, unsigned int *counts, int n_tiles, cudaStream_t stream);
+
 cudaError_t launch_u8_to_float(const uint8_t *src, int src_stride, float *dst, int dst_stride,
                                int width, int height, cudaStream_t stream);
 cudaError_t launch_export_plane(const float *src, int src_stride_floats, int comps, int comp,

@@ -155,26 +155,30 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   const int lane = threadIdx.x, wid = threadIdx.y;   // warp `wid` owns pixel row `wid` of the tile
   const int tid = wid * TILE_W + lane;
   const int pix = tid;
-  // ---- which tile, and which share of it.  A frame's duration is bounded below
-  // by its busiest tile (up to 9216 work items on one CTA) once most seeds have
-  // converged, so a tile that was much busier than the per-slot average in the
-  // PREVIOUS frame is processed by zeff CTAs, each taking every zeff-th round
-  // of its work list.  CTAs [0, n_tiles) are the tiles' lead CTAs; CTAs beyond
-  // are helpers that look up their (tile, share, zeff) in a list the lead CTAs
-  // wrote during the previous frame -- no empty grid layers to dispatch.
-  int tile, z, zeff;
-  if((int)blockIdx.x < P.n_tiles)
+  if(blockIdx.x == 0 && tid == 0)
   {
-    tile = (int)blockIdx.x;
-    z = 0;
-    zeff = (P.split_max > 1) ? max(1, P.tile_zeff_cur[tile]) : 1;
+    *P.converged_next = 0u;
+    P.counts_zero[0] = 0u; P.counts_zero[1] = 0u; P.counts_zero[2] = 0u; P.counts_zero[3] = 0u;
   }
-  else
+  // ---- which tile, and which share of it.  The lead CTAs of the PREVIOUS frame
+  // wrote this frame's work list: tiles that were busy come first (a frame ends
+  // when its slowest CTA does, so those must start at once), and a tile that
+  // was much busier than the per-slot average is listed zeff times -- its lead
+  // CTA and zeff - 1 helpers, each taking every zeff-th round of its work
+  // list (once most seeds have converged a frame's duration is bounded below by
+  // its busiest tile, up to 9216 items).  Light tiles follow; tiles with
+  // nothing left to update, ever, are not listed; surplus CTAs exit.
+  int tile, z, zeff;
   {
-    const int h = (int)blockIdx.x - P.n_tiles;
-    if(h >= min((int)*P.helper_count_cur, P.helper_cap))
+    const unsigned int n_heavy = P.counts_cur[0], n_light = P.counts_cur[1];
+    const unsigned int b = blockIdx.x;
+    unsigned int e;
+    if(b < n_heavy)
+      e = P.heavy_cur[b];
+    else if(b - n_heavy < n_light)
+      e = P.light_cur[b - n_heavy];
+    else
       return;
-    const unsigned int e = P.helper_list_cur[h];
     tile = (int)(e & 0xfffffu);
     z = (int)((e >> 20) & 0x3fu);
     zeff = (int)(e >> 26);
@@ -182,13 +186,6 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   const int x0 = (tile % P.tiles_x) * TILE_W, y0 = (tile / P.tiles_x) * TILE_H;
   const int x = x0 + lane, y = y0 + wid;
   const bool lead = (z == 0);  // the CTA that records what all of them compute identically
-
-  if(blockIdx.x == 0 && tid == 0)
-  {
-    *P.converged_next = 0u;
-    *P.frame_items_zero = 0u;
-    *P.helper_count_zero = 0u;
-  }
 
   // debug timeline (RMD_OPT_DEBUG_TIMELINE), lead CTA only:
   // [0] globaltimer ns at start, [1..4] SM cycles since start after classification /
@@ -240,26 +237,33 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     if(lead && !active && state != prev)
       *conv_ptr = state;
   }
-  if(lead)
-  {
-    const unsigned int ballot = __ballot_sync(0xffffffffu, converged);
-    if(lane == 0 && ballot)
-      atomicAdd(P.converged_now, (unsigned int)__popc(ballot));
-  }
   if(tid == 0)
   {
     S.bbox[0] = INT_MAX; S.bbox[1] = INT_MAX; S.bbox[2] = INT_MIN; S.bbox[3] = INT_MIN;
     S.items_acc = 0;
     mbar_init(&S.mbar, 1);
   }
+  const unsigned int conv_ballot = __ballot_sync(0xffffffffu, converged);
   const int n_active = __syncthreads_count(active);
   if(n_active == 0)
   {
-    if(lead && tid == 0 && P.split_max > 1)
-      P.tile_zeff_next[tile] = 1;
+    // Nothing to search.  If, moreover, every seed is in an absorbing state the
+    // tile is finished for good: it leaves the work list and its converged
+    // seeds are counted once in the retired total instead of every frame.
+    const bool pending = inside && !(state == RMD_BORDER || state == RMD_CONVERGED || state == RMD_DIVERGED);
+    const int any_pending = __syncthreads_or(pending);
+    if(lead)
+    {
+      if(lane == 0 && conv_ballot)
+        atomicAdd(any_pending ? P.converged_now : P.retired_converged, (unsigned int)__popc(conv_ballot));
+      if(tid == 0 && any_pending)
+        P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
+    }
     if(stamps && tid == 0) stamps[1] = -(clock64() - stamp_t0);
     return;
   }
+  if(lead && lane == 0 && conv_ballot)
+    atomicAdd(P.converged_now, (unsigned int)__popc(conv_ballot));
   RMD_STAMP(1);
 
   // ---- 1. search segments, candidate counts, bounding box
@@ -279,11 +283,29 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     // everything outside it is skipped wholesale and seeds whose projection left
     // the image cost no work items.  The range is estimated in closed form and
     // then fixed EXACTLY by testing the real candidates around the estimate.
+    // l only grows, so a block of 16 additions needs one end test, not 16:
+    // the same additions in the same order as the reference's loop, a fifth of
+    // the instructions of the naive transcription.
     {
       int k = 0;
-      for(float l = -seg.half_len; l <= seg.half_len; l += RMD_EPIPOLAR_STEP, ++k)
-        if((k & (L_CHECKPOINT_STEP - 1)) == 0)
-          S.l_checkpoint[pix][k / L_CHECKPOINT_STEP] = l;
+      float l = -seg.half_len;
+      while(l <= seg.half_len && k < L_CHECKPOINT_STEP * L_CHECKPOINTS)
+      {
+        S.l_checkpoint[pix][k / L_CHECKPOINT_STEP] = l;
+        float l_blk = l;
+#pragma unroll
+        for(int t = 0; t < L_CHECKPOINT_STEP; ++t) l_blk += RMD_EPIPOLAR_STEP;
+        if(l_blk <= seg.half_len)
+        {
+          l = l_blk;              // candidates k .. k+16 all exist
+          k += L_CHECKPOINT_STEP;
+          continue;
+        }
+        int t = 1;                // the last candidate is k + t - 1, 1 <= t <= 16
+        for(l += RMD_EPIPOLAR_STEP; t < L_CHECKPOINT_STEP && l <= seg.half_len; l += RMD_EPIPOLAR_STEP) ++t;
+        k += t;
+        break;
+      }
       n_cand = k;
     }
     if(n_cand > 0)
@@ -401,23 +423,27 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   RMD_STAMP(2);
   if(lead && tid == 0)
   {
-    if(P.split_max > 1)
+    // this tile's entries in the NEXT frame's work list
+    const int items = S.items_acc;
+    atomicAdd(P.counts_next + 3, (unsigned int)items);
+    const unsigned int avg_per_slot = P.counts_cur[3] / (unsigned int)P.cta_slots;
+    int znext = 1;
+    if(P.split_max > 1 && items > P.split_min_items && (unsigned int)items > 2u * avg_per_slot)
+      znext = min(P.split_max, (items + P.split_items_per_cta - 1) / P.split_items_per_cta);
+    if(znext > 1)
     {
-      // this tile's share count for the NEXT frame, and its helper CTAs
-      const int items = S.items_acc;
-      atomicAdd(P.frame_items_next, (unsigned int)items);
-      const unsigned int avg_per_slot = *P.frame_items_prev / (unsigned int)P.cta_slots;
-      int znext = 1;
-      if(items > P.split_min_items && (unsigned int)items > 2u * avg_per_slot)
-        znext = min(P.split_max, (items + P.split_items_per_cta - 1) / P.split_items_per_cta);
-      if(znext > 1)
-      {
-        const int base = (int)atomicAdd(P.helper_count_next, (unsigned int)(znext - 1));
-        znext = 1 + max(0, min(znext - 1, P.helper_cap - base));   // what fits in the list
-        for(int k = 1; k < znext; ++k)
-          P.helper_list_next[base + k - 1] = (unsigned int)tile | ((unsigned int)k << 20) | ((unsigned int)znext << 26);
-      }
-      P.tile_zeff_next[tile] = znext;
+      const int reserved = (int)atomicAdd(P.counts_next + 2, (unsigned int)(znext - 1));
+      znext = 1 + max(0, min(znext - 1, P.helper_cap - reserved));   // what fits in the list
+    }
+    if(znext > 1 || items >= P.heavy_min_items)
+    {
+      const unsigned int base = atomicAdd(P.counts_next + 0, (unsigned int)znext);
+      for(int k = 0; k < znext; ++k)
+        P.heavy_next[base + k] = (unsigned int)tile | ((unsigned int)k << 20) | ((unsigned int)znext << 26);
+    }
+    else
+    {
+      P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
     }
     if(stamps) stamps[7] = S.items_acc;
   }
@@ -784,8 +810,8 @@ static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, 
     if(device >= 0 && device < 64) configured[device] = true;
   }
   const dim3 block(TILE_W, NWARPS);
-  const dim3 grid(P.n_tiles + (P.split_max > 1 ? P.helper_cap : 0));
-  depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);  // grid.z = P.split_max
+  const dim3 grid(P.n_tiles + P.helper_cap);  // capacity of the work list; surplus CTAs exit at once
+  depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);
   return cudaGetLastError();
 }
 

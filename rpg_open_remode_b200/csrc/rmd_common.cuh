@@ -101,23 +101,26 @@ struct FilterParams
   unsigned int *converged_now;   // counter of this frame
   unsigned int *converged_next;  // counter to clear for the next frame
   long long *timeline;           // debug: 8 clock64() stamps per CTA of the staged kernel, or null
-  // staged kernel, busy-tile splitting (depth_filter_staged.cu)
-  int split_max;                         // grid.z; 1 = never split
+  // staged kernel: per-frame work list and busy-tile splitting (depth_filter_staged.cu)
+  int split_max;                         // most CTAs sharing one tile; 1 = never split
   int split_min_items, split_items_per_cta, sparse_max_seeds;  // tuning (staged_maps.cuh defaults)
+  int heavy_min_items;                   // tiles with at least this many items are dispatched first
   int cta_slots;                         // resident CTAs of the whole GPU (SMs x CTAs per SM)
   unsigned long long *tile_keys;         // [tiles][256] partial arg-max keys of split tiles
   unsigned int *tile_arrivals;           // [tiles] CTAs of a split tile that finished searching
   int n_tiles, tiles_x;                  // tile grid of the image
-  const int *tile_zeff_cur;              // [tiles] CTAs sharing each tile in this frame (0/1 = one)
-  int *tile_zeff_next;                   // [tiles] ... decided now for the next frame
-  const unsigned int *helper_list_cur;   // helper CTAs of this frame: tile | share << 20 | zeff << 26
-  unsigned int *helper_list_next;
-  const unsigned int *helper_count_cur;  // entries of helper_list_cur
-  unsigned int *helper_count_next, *helper_count_zero;
-  int helper_cap;                        // capacity of the helper lists = helper CTAs launched
-  const unsigned int *frame_items_prev;  // work items of the whole previous frame
-  unsigned int *frame_items_next;        // ... accumulated this frame
-  unsigned int *frame_items_zero;        // slot to clear for the next frame
+  // Work list of this frame, written by the lead CTAs of the previous frame.
+  // Entry = tile | share << 20 | zeff << 26.  CTA b takes heavy_cur[b], then
+  // light_cur[b - n_heavy]; CTAs beyond both lists exit.  Tiles whose seeds
+  // are all in absorbing states are not listed again (their converged seeds
+  // are counted once in *retired_converged).
+  const unsigned int *heavy_cur, *light_cur;
+  unsigned int *heavy_next, *light_next;
+  // {heavy entries, light entries, helper entries reserved, work items of the frame}
+  const unsigned int *counts_cur;
+  unsigned int *counts_next, *counts_zero;
+  unsigned int *retired_converged;
+  int helper_cap;                        // most helper entries per frame
 };
 
 } // namespace rmdb

@@ -20,12 +20,14 @@ for k in range(1, 131):
     if k in (4, 40, 130):
         s.sync()
         t = s.downloadTimeline()
+        n_all = len(t)
+        t = t[t[:, 0] > 0]          # tiles on this frame's work list (retired tiles are not launched)
         ms = s.lastKernelMs()
         act = t[:, 1] > 0
         start = t[:, 0] - t[:, 0].min()
         end = t[:, 5] - t[:, 0].min()
         dur_ns = (t[:, 5] - t[:, 0])[act]
-        print(f"frame {k}: kernel {ms*1e3:.1f} us; CTAs {len(t)}, active {act.sum()}, items total {t[:,7].sum()}, "
+        print(f"frame {k}: kernel {ms*1e3:.1f} us; tiles {n_all}, listed {len(t)}, active {act.sum()}, items total {t[:,7].sum()}, "
               f"span of starts {start.max()/1e3:.1f} us, last end {end[act].max()/1e3 if act.any() else 0:.1f} us")
         if act.any():
             ph = t[act][:, 1:5].astype(np.float64)
