@@ -423,6 +423,9 @@ def main():
         if out is not None:
             emit(out)
         return
+    # ingest-copy helper threads of the library: share the host's cores between the ranks of this node
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("RMD_COPY_THREADS", str(max(3, min(15, (os.cpu_count() or 8) // (2 * max(1, local_world)) - 1))))
     if world > 1:
         import torch
         import torch.distributed as dist

@@ -71,7 +71,7 @@ enum rmd_field {
   RMD_FIELD_CONST_TEMPL_DENOM = 6, /* float   downloadConstTemplDenom         :222 */
   RMD_FIELD_EPIPOLAR_MATCHES = 7,  /* float2  downloadEpipolarMatches         :226 */
   RMD_FIELD_REF_IMG = 8,           /* float   the reference image as uploaded */
-  RMD_FIELD_DEBUG_TIMELINE = 100   /* int64[8] per CTA, see RMD_OPT_DEBUG_TIMELINE */
+  RMD_FIELD_DEBUG_TIMELINE = 100   /* int64[16] per tile, see RMD_OPT_DEBUG_TIMELINE */
 };
 
 enum rmd_seeds_option {
@@ -85,10 +85,10 @@ enum rmd_seeds_option {
   /* fractional bits of the bilinear weights of the current-image taps
    * (8 = what the texture unit of the reference path uses; 0 = exact fp32). */
   RMD_OPT_TEX_FRAC_BITS = 2,
-  /* debug: the staged kernel records 8 x int64 per CTA (clock64 at its phase
-   * boundaries, SM id, active seeds, work items); read them back with
-   * rmd_seeds_download(h, RMD_FIELD_DEBUG_TIMELINE, dst) where dst holds
-   * 8 * ceil(w/32) * ceil(h/8) int64 values. */
+  /* debug: the staged kernel records 16 x int64 per 32x8 tile (clock64 at its
+   * phase boundaries, SM id, work items, strip coverage ...); read them back
+   * with rmd_seeds_download(h, RMD_FIELD_DEBUG_TIMELINE, dst) where dst holds
+   * 16 * ceil(w/32) * ceil(h/8) int64 values. */
   RMD_OPT_DEBUG_TIMELINE = 3,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */
@@ -96,7 +96,8 @@ enum rmd_seeds_option {
   RMD_OPT_TUNE_SPLIT_MIN_ITEMS = 11,
   RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA = 12,
   RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13,
-  RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14
+  RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14,
+  RMD_OPT_TUNE_SPLIT_AVG_PCT = 15
 };
 
 typedef struct rmd_seeds rmd_seeds_t;
@@ -189,6 +190,13 @@ int rmd_seeds_launch_count(rmd_seeds_t *s, uint64_t *fused, uint64_t *total);
  * with CUDA events on the handle's stream (blocks until it finished). */
 int rmd_seeds_last_kernel_ms(rmd_seeds_t *s, float *ms);
 int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on);
+/* Debug: host-side time of the streaming ingest, accumulated over all handles
+ * of the process when the environment variable RMD_HOST_PROFILE is set:
+ * out[0] wait for a free ring slot, [1] copy into pinned memory, [2] enqueue
+ * the host-to-device copy, [3] encode TMA descriptors, [4] launch,
+ * [5] whole rmd_seeds_update* call (all seconds), [6] number of calls.
+ * reset != 0 clears the accumulators after reading. */
+int rmd_debug_host_profile(double out[8], int reset);
 
 /* -------------------------------------------------------------- denoiser */
 

@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librmd_b200.so")
+# RMD_B200_LIB: load another build of the same library (e.g. the debug-counter build of tools/)
+LIB_PATH = os.environ.get("RMD_B200_LIB") or os.path.join(_HERE, "librmd_b200.so")
 
 vp, ci, cf, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 u64 = ctypes.c_uint64
@@ -44,6 +45,7 @@ _SIGNATURES = {
     "rmd_seeds_launch_count": (ci, [vp, P(u64), P(u64)]),
     "rmd_seeds_last_kernel_ms": (ci, [vp, P(cf)]),
     "rmd_seeds_enable_kernel_timing": (ci, [vp, ci]),
+    "rmd_debug_host_profile": (ci, [P(ctypes.c_double), ci]),
     "rmd_denoiser_create": (ci, [ci, ci, ci, P(vp)]),
     "rmd_denoiser_destroy": (ci, [vp]),
     "rmd_denoiser_set_stream": (ci, [vp, vp]),

@@ -351,9 +351,9 @@ class SeedMatrix:
         return a
 
     def downloadTimeline(self):
-        """Debug (OPT_DEBUG_TIMELINE): int64[n_ctas, 8] of the last staged launch."""
+        """Debug (OPT_DEBUG_TIMELINE): int64[n_tiles, 16] of the last staged launch."""
         n = ((self.width_ + 31) // 32) * ((self.height_ + 7) // 8)
-        out = np.empty((n, 8), np.int64)
+        out = np.empty((n, 16), np.int64)
         check(self._L.rmd_seeds_download(self._h, FIELD_DEBUG_TIMELINE, out.ctypes.data), "SeedMatrix::downloadTimeline")
         return out
 

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <string>
@@ -77,6 +78,37 @@ static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; 
 
 using namespace rmdb;
 
+// ------------------------------------------------ host profile (debug)
+namespace
+{
+double g_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+const bool g_prof_on = (getenv("RMD_HOST_PROFILE") != NULL);
+
+struct ProfScope
+{
+  int idx;
+  std::chrono::steady_clock::time_point t0;
+  explicit ProfScope(int i) : idx(i)
+  {
+    if(g_prof_on) t0 = std::chrono::steady_clock::now();
+  }
+  ~ProfScope()
+  {
+    if(g_prof_on)
+      g_prof[idx] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+} // namespace
+
+int rmd_debug_host_profile(double out[8], int reset)
+{
+  RMD_REQUIRE(out, "rmd_debug_host_profile: null argument");
+  for(int i = 0; i < 8; ++i) out[i] = g_prof[i];
+  if(reset)
+    for(int i = 0; i < 8; ++i) g_prof[i] = 0.0;
+  return 0;
+}
+
 // =========================================================== seed matrix
 
 static const int kSlots = 3;
@@ -135,7 +167,7 @@ struct rmd_seeds
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  int tune[5];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items
+  int tune[6];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
 };
 
@@ -308,7 +340,7 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.tile_keys = s->tile_keys;
     P.tile_arrivals = s->tile_arrivals;
     P.n_tiles = s->n_tiles; P.tiles_x = s->tiles_x; P.helper_cap = staged::HELPER_CAP;
-    P.heavy_min_items = s->tune[4];
+    P.heavy_min_items = s->tune[4]; P.split_avg_pct = s->tune[5];
     P.heavy_cur = s->heavy_list[(f + 1) & 1]; P.heavy_next = s->heavy_list[f & 1];
     P.light_cur = s->light_list[(f + 1) & 1]; P.light_next = s->light_list[f & 1];
     P.counts_cur = s->work_counts + 4 * ((f + 2) % 3);
@@ -321,8 +353,12 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   if(s->variant == 0)
   {
     if(!s->maps) s->maps = new StagedMaps();
-    const int rc = s->maps->encode(P, s->patch);
-    if(rc) return rc;
+    {
+      ProfScope prof(3);
+      const int rc = s->maps->encode(P, s->patch);
+      if(rc) return rc;
+    }
+    ProfScope prof_launch(4);
     if(!s->worklist_valid)
     {
       // every tile once, in image order, no helpers; nothing retired yet
@@ -362,16 +398,27 @@ int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *
   s->next_slot = (slot + 1) % kSlots;
   const size_t row_bytes = elem_size * (size_t)s->width;
   if(s->slot_used[slot])
+  {
+    ProfScope prof(0);
     RMD_CUDA_TRY(cudaEventSynchronize(s->copied[slot]));  // pinned buffer free again
+  }
   if(!s->copier)
   {
-    const char *env = getenv("RMD_COPY_THREADS");   // helper threads for the ingest copy (default 3)
-    int helpers = env ? atoi(env) : 3;
+    // helper threads for the ingest copy: RMD_COPY_THREADS, else an eighth of the
+    // machine (3..15).  One core stages a cold 1.2 MB frame in ~95 us, 4 in ~31 us,
+    // 16 in ~13 us (tools/copy_probe.cpp on the B200 host, 128 hardware threads).
+    const char *env = getenv("RMD_COPY_THREADS");
+    int helpers = env ? atoi(env) : (int)(std::thread::hardware_concurrency() / 8) - 1;
+    if(!env && helpers < 3) helpers = 3;
     if(helpers < 0) helpers = 0;
     if(helpers > 15) helpers = 15;
     s->copier = new ParallelCopier(helpers);
   }
-  s->copier->copy(s->pinned[slot], host_img, row_bytes * s->height);
+  {
+    ProfScope prof(1);
+    s->copier->copy(s->pinned[slot], host_img, row_bytes * s->height);
+  }
+  ProfScope prof_h2d(2);
   if(s->slot_used[slot])
     RMD_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->consumed[slot], 0));
   if(elem_size == sizeof(float))
@@ -469,7 +516,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tex_frac_bits = 8;
   s->tune[0] = staged::SPLIT_MAX; s->tune[1] = staged::SPLIT_MIN_ITEMS;
   s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
-  s->tune[4] = staged::HEAVY_MIN_ITEMS;
+  s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT;
   s->variant = 1;
   const int rc = seeds_alloc(s);
   if(rc)
@@ -522,7 +569,7 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     DeviceGuard guard(s->device);
     if(value && !s->timeline)
     {
-      s->timeline_bytes = sizeof(long long) * 8 * (size_t)((s->width + 31) / 32) * (size_t)((s->height + 7) / 8);
+      s->timeline_bytes = sizeof(long long) * 16 * (size_t)((s->width + 31) / 32) * (size_t)((s->height + 7) / 8);
       RMD_CUDA_TRY(cudaMalloc(&s->timeline, s->timeline_bytes));
       RMD_CUDA_TRY(cudaMemset(s->timeline, 0, s->timeline_bytes));
     }
@@ -535,9 +582,9 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     return 0;
   }
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
-  case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS:
+  case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT:
     RMD_REQUIRE(value >= (option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS ? 0 : 1) && value <= 65535, "tuning value out of range");
-    RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 16, "RMD_OPT_TUNE_SPLIT_MAX: 1..16");
+    RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
     return 0;
   case RMD_OPT_TEX_FRAC_BITS:
@@ -594,6 +641,8 @@ int rmd_seeds_update(rmd_seeds_t *s, const float *host_img, const float *T_curr_
   RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_update: null argument");
   if(!s->has_reference)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update: set_reference has not been called");
+  ProfScope prof(5);
+  if(g_prof_on) g_prof[6] += 1.0;
   DeviceGuard guard(s->device);
   int slot = 0;
   const int rc = stage_host_frame(s, host_img, sizeof(float), &slot);
@@ -609,6 +658,8 @@ int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_
   RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_update_u8: null argument");
   if(!s->has_reference)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_u8: set_reference has not been called");
+  ProfScope prof(5);
+  if(g_prof_on) g_prof[6] += 1.0;
   DeviceGuard guard(s->device);
   int slot = 0;
   const int rc = stage_host_frame(s, host_img, sizeof(uint8_t), &slot);

@@ -36,6 +36,13 @@
 #include "depth_filter_math.cuh"
 #include "staged_maps.cuh"
 
+// 1: the debug timeline also counts the candidates scored from the strip and
+// from global memory (slots 8, 9).  Off by default: even predicated off, the
+// counters cost the search-heavy frames ~15 %.
+#ifndef RMD_DEBUG_COUNTERS
+#define RMD_DEBUG_COUNTERS 0
+#endif
+
 namespace rmdb
 {
 
@@ -57,11 +64,15 @@ struct __align__(128) StagedSmem
   float ref[REF_BOX_W * ref_box_h(PS)];
   SearchRec rec[NPIX];
   unsigned long long best[NPIX];
-  int level_total[TILE_H];
+  int n_levels;                        // chunks of the tile's longest search
+  int dbg[8];                          // debug build (RMD_DEBUG_COUNTERS): see the timeline slots 8.. below
   float l_checkpoint[NPIX][L_CHECKPOINTS];  // l of candidates 0, 16, 32, ... of every seed
-  unsigned int level_mask[TILE_H][MAX_CHUNKS + 2];
-  int level_cum[TILE_H][MAX_CHUNKS + 2];
+  // tile-wide chunk-major work list: level c = the seeds that have a c-th chunk
+  unsigned int level_mask[MAX_CHUNKS][TILE_H];              // ... as one ballot per pixel row
+  __align__(16) unsigned short level_rowpre[MAX_CHUNKS][TILE_H];  // items of level c in the rows above
+  int level_cum[MAX_CHUNKS + 4];                            // items before level c; [n_levels] = all items
   int bbox[4];       // xmin, ymin, xmax, ymax over all segments of the CTA
+  int centroid[3];   // sum of x * w, y * w, w over the seeds (w = accepted candidates, x/y = middle of their range)
   int strip_ox, strip_oy, strip_w, strip_rows;
   int is_last;
   int items_acc;                       // work items of the tile (sum of the seeds' chunk counts)
@@ -128,6 +139,7 @@ __device__ __forceinline__ unsigned int orderable(float f)
 // Texel block of a candidate inside the shared-memory strip.
 struct StripTaps
 {
+  static constexpr bool kEdgeFirst = false;
   const float *origin;
   int stride;
   __device__ __forceinline__ StripTaps(const float *strip, int strip_w, int ox, int oy, const TapFrame &t)
@@ -170,11 +182,14 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   // nothing left to update, ever, are not listed; surplus CTAs exit.
   int tile, z, zeff;
   {
-    const unsigned int n_heavy = P.counts_cur[0], n_light = P.counts_cur[1];
     const unsigned int b = blockIdx.x;
+    // (the heavy list has one slot per launched CTA: load the entry together with
+    // the counts -- one memory round trip instead of two for the busy tiles)
+    const unsigned int e_heavy = P.heavy_cur[b];
+    const unsigned int n_heavy = P.counts_cur[0], n_light = P.counts_cur[1];
     unsigned int e;
     if(b < n_heavy)
-      e = P.heavy_cur[b];
+      e = e_heavy;
     else if(b - n_heavy < n_light)
       e = P.light_cur[b - n_heavy];
     else
@@ -190,8 +205,10 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   // debug timeline (RMD_OPT_DEBUG_TIMELINE), lead CTA only:
   // [0] globaltimer ns at start, [1..4] SM cycles since start after classification /
   // search set-up / TMA arrival / NCC search, [5] globaltimer ns at the end,
-  // [6] SM id, [7] work items of the tile
-  long long *const stamps = (P.timeline && lead) ? P.timeline + 8 * (size_t)tile : nullptr;
+  // [6] SM id, [7] work items of the tile, [8] candidates scored from the strip,
+  // [9] ... from global memory, [10] bounding box w | h << 16, [11] strip w | rows << 16,
+  // [12] seeds to update, [13] zeff | sparse << 8
+  long long *const stamps = (P.timeline && lead) ? P.timeline + 16 * (size_t)tile : nullptr;
   const long long stamp_t0 = stamps ? clock64() : 0;
 #define RMD_STAMP(i) do { if(stamps && tid == 0) { if((i) == 5) { long long gt_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[5] = gt_; } \
@@ -217,7 +234,9 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   if(inside)
   {
     conv_ptr = P.conv + (size_t)y * P.conv_stride + x;
+    seed_ptr = P.seed + (size_t)y * P.seed_stride + x;
     prev = *conv_ptr;
+    seed = *seed_ptr;   // issued with the state load, not after it: one memory round trip for the tile
     if(P.trust_conv && (prev == RMD_BORDER || prev == RMD_CONVERGED || prev == RMD_DIVERGED))
     {
       state = prev;
@@ -228,8 +247,6 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     }
     else
     {
-      seed_ptr = P.seed + (size_t)y * P.seed_stride + x;
-      seed = *seed_ptr;
       state = classify_seed(P, seed);
       active = (state == RMD_UPDATE);
     }
@@ -241,6 +258,9 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   {
     S.bbox[0] = INT_MAX; S.bbox[1] = INT_MAX; S.bbox[2] = INT_MIN; S.bbox[3] = INT_MIN;
     S.items_acc = 0;
+    S.n_levels = 0;
+    for(int i = 0; i < 8; ++i) S.dbg[i] = 0;
+    S.centroid[0] = 0; S.centroid[1] = 0; S.centroid[2] = 0;
     mbar_init(&S.mbar, 1);
   }
   const unsigned int conv_ballot = __ballot_sync(0xffffffffu, converged);
@@ -273,6 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   int bx_lo = INT_MAX, by_lo = INT_MAX, bx_hi = INT_MIN, by_hi = INT_MIN;
   if(active)
   {
+    const float2 stats = __ldg(P.templ + (size_t)y * P.templ_stride + x);
     seg = epipolar_segment(P, x, y, seed.x, seed.y);
     // The candidate positions follow the reference's own float accumulation of l
     // (epipolar_match.cu:88).  One cheap pass counts them and records l every
@@ -392,7 +413,6 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     {
       bx_lo = xl; bx_hi = xh; by_lo = yl; by_hi = yh;
     }
-    const float2 stats = __ldg(P.templ + (size_t)y * P.templ_stride + x);
     SearchRec r;
     r.mean_x = seg.mean.x; r.mean_y = seg.mean.y; r.dir_x = seg.dir.x; r.dir_y = seg.dir.y;
     r.half_len = seg.half_len; r.sum_templ = stats.x; r.denom = stats.y;
@@ -405,10 +425,15 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   {
     const unsigned int act = __ballot_sync(0xffffffffu, active);
     const int m_row = __reduce_add_sync(0xffffffffu, m_chunks);
+    const int m_max = __reduce_max_sync(0xffffffffu, m_chunks);
     if(lane == 0)
     {
       S.row_active[wid] = act;
-      if(m_row) atomicAdd(&S.items_acc, m_row);
+      if(m_row)
+      {
+        atomicAdd(&S.items_acc, m_row);
+        atomicMax(&S.n_levels, m_max);
+      }
     }
   }
   bx_lo = __reduce_min_sync(0xffffffffu, bx_lo); by_lo = __reduce_min_sync(0xffffffffu, by_lo);
@@ -417,6 +442,24 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   {
     atomicMin(&S.bbox[0], bx_lo); atomicMin(&S.bbox[1], by_lo);
     atomicMax(&S.bbox[2], bx_hi); atomicMax(&S.bbox[3], by_hi);
+  }
+  {
+    // where the candidates are, for the strip placement when the box is larger than the strip
+    int w = 0, wx = 0, wy = 0;
+    if(k_hi >= 0)
+    {
+      w = k_hi - k_lo + 1;
+      const float l_mid = -seg.half_len + RMD_EPIPOLAR_STEP * 0.5f * (float)(k_lo + k_hi);
+      wx = w * to_int_clamped(seg.mean.x + l_mid * seg.dir.x);
+      wy = w * to_int_clamped(seg.mean.y + l_mid * seg.dir.y);
+    }
+    w = __reduce_add_sync(0xffffffffu, w);
+    wx = __reduce_add_sync(0xffffffffu, wx);
+    wy = __reduce_add_sync(0xffffffffu, wy);
+    if(lane == 0 && w > 0)
+    {
+      atomicAdd(&S.centroid[0], wx); atomicAdd(&S.centroid[1], wy); atomicAdd(&S.centroid[2], w);
+    }
   }
   __syncthreads();
 
@@ -427,9 +470,16 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     const int items = S.items_acc;
     atomicAdd(P.counts_next + 3, (unsigned int)items);
     const unsigned int avg_per_slot = P.counts_cur[3] / (unsigned int)P.cta_slots;
+    // CTAs in proportion to the tile's share of the frame: about one resident-CTA
+    // slot's worth of items each (never fewer than split_items_per_cta, the fixed
+    // cost of a CTA must pay off), so the frame's CTAs finish together and the sum
+    // of all helpers stays below the number of slots.
     int znext = 1;
-    if(P.split_max > 1 && items > P.split_min_items && (unsigned int)items > 2u * avg_per_slot)
-      znext = min(P.split_max, (items + P.split_items_per_cta - 1) / P.split_items_per_cta);
+    if(P.split_max > 1 && items > P.split_min_items)
+    {
+      const unsigned int target = max((unsigned int)P.split_items_per_cta, avg_per_slot * (unsigned int)P.split_avg_pct / 100u);
+      znext = (int)min((unsigned int)P.split_max, ((unsigned int)items + target - 1u) / target);
+    }
     if(znext > 1)
     {
       const int reserved = (int)atomicAdd(P.counts_next + 2, (unsigned int)(znext - 1));
@@ -445,7 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     {
       P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
     }
-    if(stamps) stamps[7] = S.items_acc;
+    if(stamps) { stamps[7] = S.items_acc; stamps[12] = n_active; }
   }
 
   // ---- sparse tile (the common case once most seeds have converged): a handful
@@ -453,6 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   // warp per seed, lanes = candidates, taps straight from global memory (L2),
   // arg-max with warp shuffles on the same (ncc, -index) key.
   const bool sparse = (n_active <= P.sparse_max_seeds) && (zeff == 1);
+  if(stamps && tid == 0) stamps[13] = zeff | (sparse ? 256 : 0);
   if(sparse)
   {
     int seen = 0;
@@ -535,10 +586,19 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       const int max_rows = (STRIP_FLOATS / sw) / STRIP_BOX_ROWS * STRIP_BOX_ROWS;
       const int want_rows = (bh + STRIP_BOX_ROWS - 1) / STRIP_BOX_ROWS * STRIP_BOX_ROWS;
       rows = min(want_rows, max_rows);
-      ox = (bw <= sw) ? xmin_a : ((xmin_a + (bw - sw) / 2) & ~3);
-      oy = (want_rows <= max_rows) ? ymin : ymin + (bh - rows) / 2;
+      // a box larger than the strip: centre the strip on the candidates' centroid
+      // (a few outliers stretch the box, most candidates cluster), inside the box
+      const int cw = max(1, S.centroid[2]);
+      const int cx = S.centroid[0] / cw, cy = S.centroid[1] / cw;
+      ox = (bw <= sw) ? xmin_a : (min(max(cx - sw / 2, xmin_a), xmax + 1 - sw + 3) & ~3);
+      oy = (want_rows <= max_rows) ? ymin : min(max(cy - rows / 2, ymin), ymax + 1 - rows);
     }
     S.strip_ox = ox; S.strip_oy = oy; S.strip_w = sw; S.strip_rows = rows;
+    if(stamps)
+    {
+      stamps[10] = (long long)max(0, xmax - xmin + 1) | ((long long)max(0, ymax - ymin + 1) << 16);
+      stamps[11] = (long long)sw | ((long long)rows << 16);
+    }
     const unsigned int ref_bytes = REF_BOX_W * ref_box_h(PS) * (unsigned int)sizeof(float);
     mbar_expect_tx(&S.mbar, ref_bytes + (unsigned int)(rows * sw) * (unsigned int)sizeof(float));
     tma_load_2d(S.ref, &M.ref, x0 - REF_ORIGIN_X, y0 - PS / 2, &S.mbar);
@@ -547,58 +607,88 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       tma_load_2d(S.strip + r * sw, cm, ox, oy + r, &S.mbar);
   }
 
-  // ---- 3. balanced NCC search: chunk-major work list per pixel row
+  // ---- 3. balanced NCC search: one chunk-major work list for the whole tile
+  // Level c of the list = all seeds of the tile that still have a c-th chunk,
+  // in pixel order; item q belongs to level c = max{c : cum[c] <= q}, and is the
+  // (q - cum[c])-th such seed.  Lanes of a round therefore work on neighbouring
+  // pixels' candidates, every round but the last is full, and a round costs
+  // the same whatever the mix of search lengths in the tile.
+  const int n_levels = S.n_levels;
   {
-    // level c of a row = the seeds that still have a c-th chunk of candidates;
-    // ballots are warp-uniform, so every lane tracks the running item count
     const int m = m_chunks;
-    int cum = 0;
-    for(int c = 0; c < MAX_CHUNKS; ++c)
+    for(int c = 0; c < n_levels; ++c)
     {
       const unsigned int mk = __ballot_sync(0xffffffffu, m > c);
       if(lane == 0)
       {
-        S.level_mask[wid][c] = mk;
-        S.level_cum[wid][c] = cum;  // items before level c
+        S.level_mask[c][wid] = mk;
+        S.level_rowpre[c][wid] = (unsigned short)__popc(mk);
       }
-      cum += __popc(mk);
-    }
-    if(lane == 0)
-    {
-      S.level_cum[wid][MAX_CHUNKS] = cum;
-      S.level_total[wid] = cum;
     }
   }
-  __syncthreads();  // publishes the work lists and the strip geometry (built while the TMA is in flight)
+  __syncthreads();
+  if(wid == 0)
+  {
+    // row counts -> exclusive row prefixes per level, level totals -> exclusive scan over the levels
+    int tot[2];
+#pragma unroll
+    for(int h = 0; h < 2; ++h)
+    {
+      const int c = lane + 32 * h;
+      int acc = 0;
+      if(c < n_levels)
+      {
+#pragma unroll
+        for(int r = 0; r < TILE_H; ++r)
+        {
+          const int cnt = S.level_rowpre[c][r];
+          S.level_rowpre[c][r] = (unsigned short)acc;
+          acc += cnt;
+        }
+      }
+      tot[h] = acc;
+    }
+    int inc0 = tot[0], inc1 = tot[1];
+#pragma unroll
+    for(int off = 1; off < 32; off <<= 1)
+    {
+      const int a0 = __shfl_up_sync(0xffffffffu, inc0, off), a1 = __shfl_up_sync(0xffffffffu, inc1, off);
+      if(lane >= off) { inc0 += a0; inc1 += a1; }
+    }
+    const int sum0 = __shfl_sync(0xffffffffu, inc0, 31);
+    if(lane <= n_levels) S.level_cum[lane] = inc0 - tot[0];                  // lane == n_levels <= 31: the total
+    if(lane + 32 <= n_levels) S.level_cum[lane + 32] = sum0 + inc1 - tot[1];
+  }
+  __syncthreads();  // publishes the work list and the strip geometry (built while the TMA is in flight)
   const int strip_ox = S.strip_ox, strip_oy = S.strip_oy, strip_w = S.strip_w, strip_rows = S.strip_rows;
   mbar_wait(&S.mbar, 0);
   RMD_STAMP(3);
-  // The warps of the tile's zeff CTAs take 32-item rounds of the rows' lists round-robin.
-  for(int rho = z * NWARPS + wid; ; rho += zeff * NWARPS)
+  // The warps of the tile's zeff CTAs take 32-item rounds of the list round-robin.
+  const int total = S.level_cum[n_levels];
+  for(int rho = z * NWARPS + wid; rho * 32 < total; rho += zeff * NWARPS)
   {
-    int r = 0, local = rho;
-#pragma unroll
-    for(int k = 0; k < TILE_H - 1; ++k)
-    {
-      const int rounds_k = (S.level_total[k] + 31) >> 5;
-      if(r == k && local >= rounds_k) { local -= rounds_k; r = k + 1; }
-    }
-    const int total = S.level_total[r];
-    if(local * 32 >= total)
-      break;
-    const int q = local * 32 + lane;
+    const int q = rho * 32 + lane;
+#if RMD_DEBUG_COUNTERS
+    const long long dbg_t0 = clock64();
+#endif
     if(q < total)
     {
-      // largest level c with level_cum[c] <= q (level_cum[MAX_CHUNKS] = total > q)
-      int c = 0, hi = MAX_CHUNKS;
+      // largest level c with level_cum[c] <= q (level_cum[n_levels] = total > q)
+      int c = 0, hi = n_levels;
 #pragma unroll
       for(int step = 0; step < 6; ++step)
       {
         const int mid = (c + hi) >> 1;
-        if(S.level_cum[r][mid] <= q) c = mid; else hi = mid;
+        if(S.level_cum[mid] <= q) c = mid; else hi = mid;
       }
-      const int rank = q - S.level_cum[r][c];
-      const int src = __fns(S.level_mask[r][c], 0, rank + 1);  // lane owning the seed
+      const int rank = q - S.level_cum[c];
+      // pixel row: the last one whose prefix does not exceed the rank (prefixes are non-decreasing)
+      const uint4 pre = *reinterpret_cast<const uint4*>(&S.level_rowpre[c][0]);
+      const int p1 = (int)(pre.x >> 16), p2 = (int)(pre.y & 0xffffu), p3 = (int)(pre.y >> 16);
+      const int p4 = (int)(pre.z & 0xffffu), p5 = (int)(pre.z >> 16), p6 = (int)(pre.w & 0xffffu), p7 = (int)(pre.w >> 16);
+      const int r = (p1 <= rank) + (p2 <= rank) + (p3 <= rank) + (p4 <= rank) + (p5 <= rank) + (p6 <= rank) + (p7 <= rank);
+      const int before = (r == 0) ? 0 : (r == 1) ? p1 : (r == 2) ? p2 : (r == 3) ? p3 : (r == 4) ? p4 : (r == 5) ? p5 : (r == 6) ? p6 : p7;
+      const int src = __fns(S.level_mask[c][r], 0, rank - before + 1);  // lane owning the seed
 
       const SearchRec R = S.rec[r * TILE_W + src];
       float templ[PS * PS];
@@ -616,6 +706,9 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
 
       float best_ncc = -1.0f;
       int best_idx = 0;
+#if RMD_DEBUG_COUNTERS
+      const long long dbg_t1 = clock64();
+#endif
 #pragma unroll 1
       for(int i = 0; i < CHUNK; ++i, l += RMD_EPIPOLAR_STEP)
       {
@@ -627,6 +720,14 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
         const bool in_strip = (frame.i0 >= strip_ox) && (frame.i0 + PS < strip_ox + strip_w) &&
                               (frame.j0 >= strip_oy) && (frame.j0 + PS < strip_oy + strip_rows);
         float ncc;
+#if RMD_DEBUG_COUNTERS
+        if(P.timeline)
+        {
+          atomicAdd(&S.dbg[in_strip ? 0 : 1], 1);                  // candidates (lanes)
+          const unsigned int am = __activemask();
+          if(lane == __ffs(am) - 1) atomicAdd(&S.dbg[in_strip ? 2 : 3], 1);  // warp-level executions of each path
+        }
+#endif
         if(in_strip)
         {
           const StripTaps taps(S.strip, strip_w, strip_ox, strip_oy, frame);
@@ -649,10 +750,28 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
             (((unsigned long long)orderable(best_ncc)) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)best_idx);
         atomicMax(&S.best[r * TILE_W + src], key);
       }
+#if RMD_DEBUG_COUNTERS
+      if(P.timeline && q == rho * 32)
+      {
+        const long long t2 = clock64();
+        atomicAdd(&S.dbg[4], (int)(dbg_t1 - dbg_t0));   // item decode: list lookup, record, template
+        atomicAdd(&S.dbg[5], (int)(t2 - dbg_t1));       // the item's candidates (first lane of the round)
+        atomicAdd(&S.dbg[6], 1);                        // rounds
+      }
+#endif
     }
   }
   __syncthreads();
   RMD_STAMP(4);
+  // debug build: [8] candidates from the strip, [9] from global memory, [14] decode cycles | rounds << 40,
+  // [15] candidate cycles of the rounds' first lanes, [13] also warp-level strip passes << 16 | global passes << 40
+  if(stamps && tid == 0)
+  {
+    stamps[8] = S.dbg[0]; stamps[9] = S.dbg[1];
+    stamps[14] = (long long)S.dbg[4] | ((long long)S.dbg[6] << 40);
+    stamps[15] = S.dbg[5];
+    stamps[13] |= ((long long)S.dbg[2] << 16) | ((long long)S.dbg[3] << 40);
+  }
   }  // staged (non-sparse) path
 
   // ---- 3b. a split tile: merge the partial arg-max of its CTAs in global

@@ -1,11 +1,12 @@
 """Where does the end-to-end (host buffer in) frame time go?  GPU box only."""
-import os, sys, time
+import os, sys, time, ctypes
+os.environ.setdefault('RMD_HOST_PROFILE', '1')
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import rpg_open_remode_b200 as rmd
-from rpg_open_remode_b200 import synth
+from rpg_open_remode_b200 import synth, _native
 
 W, H, N = 640, 480, 200
 seq = synth.SyntheticSequence(W, H, seed=0x5EED0002)
@@ -44,6 +45,12 @@ def run(label, variant, use_u8=False):
         s.sync()
         t_all = time.perf_counter() - t0
     call = np.array(call) * 1e6
+    prof = (ctypes.c_double * 8)()
+    _native.lib().rmd_debug_host_profile(prof, 1)
+    if prof[6] > 0:
+        n = prof[6]
+        print("    host profile per call (us): wait-slot %.1f  pinned-copy %.1f  h2d-enqueue %.1f  tma-encode %.1f  launch %.1f  total %.1f  (%d calls)" %
+              (*(prof[i] / n * 1e6 for i in range(6)), int(n)))
     print("%-34s total %.2f ms (%.0f fps)  enqueue %.2f ms  per-call median %.1f us p90 %.1f max %.1f" %
           (label, t_all * 1e3, (N - 1) / t_all, t_enq * 1e3, np.median(call), np.percentile(call, 90), call.max()))
 

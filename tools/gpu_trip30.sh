@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_full.log 2>&1
+timeout 600 python tools/timeline_probe.py > gpurun_out/timeline.txt 2>&1
+RMD_B200_LIB=$PWD/tools/build/librmd_b200_dbg.so timeout 600 python tools/timeline_probe.py > gpurun_out/timeline_dbg.txt 2>&1
+timeout 900 python tools/tune_probe.py > gpurun_out/tune_probe.txt 2>&1
+timeout 600 python tools/e2e_probe.py > gpurun_out/e2e_probe.txt 2>&1
+timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_staged.json 2> gpurun_out/bench_staged.err
+echo done

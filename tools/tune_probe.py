@@ -18,7 +18,7 @@ d_frames = torch.from_numpy(frames).to(dev)
 g = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera)); g.setStream(stream.cuda_stream); g.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED)
 
 def run(cfg):
-    for opt, val in zip((10, 11, 12, 13, 14), cfg): g.setOption(opt, val)
+    for opt, val in zip((10, 11, 12, 13, 14, 15), cfg): g.setOption(opt, val)
     best = 1e9; seg = None
     for rep in range(4):
         g.setReferenceImageDevice(d_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)
@@ -33,9 +33,9 @@ def run(cfg):
             best = tot; seg = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
     return best, seg
 
-for cfg in [(8, 512, 256, 16, 48), (1, 512, 256, 16, 48), (8, 512, 256, 16, 65535), (8, 512, 256, 16, 1), (8, 512, 256, 16, 16),
-            (8, 512, 256, 16, 128), (8, 192, 128, 16, 48), (8, 128, 64, 16, 48), (8, 96, 48, 16, 32), (16, 128, 64, 16, 48),
-            (8, 256, 128, 0, 48), (8, 256, 128, 8, 48), (8, 256, 128, 32, 48)]:
+for cfg in [(16, 512, 256, 16, 48, 100), (1, 512, 256, 16, 48, 100), (8, 512, 256, 16, 48, 100), (32, 512, 256, 16, 48, 100),
+            (16, 512, 256, 16, 48, 200), (16, 512, 256, 16, 48, 50), (16, 256, 256, 16, 48, 100), (16, 256, 128, 16, 48, 100),
+            (16, 384, 192, 16, 48, 100), (16, 512, 384, 16, 48, 100), (16, 512, 256, 8, 48, 100), (16, 512, 256, 16, 24, 100)]:
     tot, seg = run(cfg)
-    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-199 %.2f ms" %
+    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-199 %.2f ms" %
           (*cfg, tot, 199 / tot * 1e3, *seg))
