@@ -97,7 +97,8 @@ enum rmd_seeds_option {
   RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA = 12,
   RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13,
   RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14,
-  RMD_OPT_TUNE_SPLIT_AVG_PCT = 15
+  RMD_OPT_TUNE_SPLIT_AVG_PCT = 15,
+  RMD_OPT_TUNE_PDL = 16            /* 1 (default): programmatic dependent launch of consecutive frames */
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

@@ -167,7 +167,7 @@ struct rmd_seeds
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  int tune[6];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct
+  int tune[7];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
 };
 
@@ -340,7 +340,7 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.tile_keys = s->tile_keys;
     P.tile_arrivals = s->tile_arrivals;
     P.n_tiles = s->n_tiles; P.tiles_x = s->tiles_x; P.helper_cap = staged::HELPER_CAP;
-    P.heavy_min_items = s->tune[4]; P.split_avg_pct = s->tune[5];
+    P.heavy_min_items = s->tune[4]; P.split_avg_pct = s->tune[5]; P.pdl = s->tune[6];
     P.heavy_cur = s->heavy_list[(f + 1) & 1]; P.heavy_next = s->heavy_list[f & 1];
     P.light_cur = s->light_list[(f + 1) & 1]; P.light_next = s->light_list[f & 1];
     P.counts_cur = s->work_counts + 4 * ((f + 2) % 3);
@@ -516,7 +516,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tex_frac_bits = 8;
   s->tune[0] = staged::SPLIT_MAX; s->tune[1] = staged::SPLIT_MIN_ITEMS;
   s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
-  s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT;
+  s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT; s->tune[6] = 1;
   s->variant = 1;
   const int rc = seeds_alloc(s);
   if(rc)
@@ -582,8 +582,8 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     return 0;
   }
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
-  case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT:
-    RMD_REQUIRE(value >= (option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS ? 0 : 1) && value <= 65535, "tuning value out of range");
+  case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT: case RMD_OPT_TUNE_PDL:
+    RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL) ? 0 : 1) && value <= 65535, "tuning value out of range");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
     return 0;

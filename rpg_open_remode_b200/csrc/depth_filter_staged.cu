@@ -1,28 +1,31 @@
 // depth_filter_staged.cu -- fused depth filter, staged variant for sm_100a.
 //
-// One CTA (8 warps) per 32x8 tile of the reference view, one warp per pixel
-// row.  Per frame (details and measurements: DESIGN.md section 4.1):
+// One CTA (8 warps) per listed 32x8 tile of the reference view, one warp per
+// pixel row.  Per frame (details and measurements: DESIGN.md section 4.1):
+//   W. the CTA looks up its tile in the frame's work list, written by the
+//      previous frame's kernel: busy tiles first, tiles that are finished for
+//      good not at all, very busy tiles several times (3b);
 //   0. classify every seed (convergence check, src/seed_check.cu:29-67);
 //      absorbing seeds cost 4 bytes, a tile with nothing to update ends here;
 //   1. every active seed projects its depth interval into the current frame
 //      (src/epipolar_match.cu:60-75), counts its candidates with the
 //      reference's own float accumulation (checkpointing l every 16th), finds
 //      the exact contiguous range of candidates inside the image, and the CTA
-//      reduces the bounding box of all search segments;
+//      reduces the bounding box and the centroid of all search segments;
 //   2. one thread issues TMA loads (cp.async.bulk.tensor.2d -> UTMALDG,
-//      mbarrier complete_tx) of the reference tile (+halo) and of the strip of
-//      the current frame under that bounding box into shared memory;
-//   3. the seeds' candidates are cut into 4-candidate chunks; per pixel row they
-//      form a chunk-major work list and all warps take 32-item rounds of the 8
-//      lists round-robin, so lanes stay busy whatever the mix of search
-//      lengths; a candidate's NCC is evaluated by the same code as in the direct
-//      variant (depth_filter_math.cuh) on taps from the shared-memory strip
-//      (from global memory for the rare block outside it); per-seed arg-max is a
+//      mbarrier complete_tx) of the reference tile (+halo) and of the strip of the
+//      current frame under that bounding box into shared memory;
+//   3. the seeds' candidates are cut into 4-candidate chunks; the tile's chunks
+//      form one chunk-major work list and all warps take 32-item rounds of it
+//      round-robin, so lanes stay busy whatever the mix of search lengths; a
+//      candidate's NCC is evaluated by the same code as in the direct variant
+//      (depth_filter_math.cuh) on taps from the shared-memory strip (from
+//      global memory for the rare block outside it); per-seed arg-max is a
 //      shared-memory 64-bit atomicMax on (ncc, -index), which reproduces the
 //      reference's "first maximum wins" (epipolar_match.cu:125-129);
-//   3b. a tile that was much busier than average in the previous frame is
-//      shared by up to 8 CTAs (helper CTAs listed by the previous frame), merged
-//      through global atomics;
+//   3b. a tile that was much busier than its share of the previous frame is
+//      processed by up to 16 CTAs (listed next to each other), merged through
+//      global atomics, the last one to arrive finalising the tile;
 //   3c. a tile with at most 16 seeds to update skips staging: one warp per seed,
 //      lanes = candidates, warp-shuffle arg-max;
 //   4. the owner thread triangulates the best match and updates its seed
@@ -164,6 +167,14 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   const unsigned int smem_pad = (128u - (smem_addr(smem_raw) & 127u)) & 127u;
   StagedSmem<PS> &S = *reinterpret_cast<StagedSmem<PS>*>(smem_raw + smem_pad);
 
+  // Launched with programmatic stream serialisation: this grid may be set up
+  // while the previous frame's kernel drains; nothing may be read before that
+  // kernel has completed and flushed (a no-op for an ordinary launch).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // pdl == 2: let the next frame's CTAs take the slots this frame's tail leaves
+  // idle (they park at their own griddepcontrol.wait until this grid is done)
+  if(P.pdl == 2)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x, wid = threadIdx.y;   // warp `wid` owns pixel row `wid` of the tile
   const int tid = wid * TILE_W + lane;
   const int pix = tid;
@@ -930,8 +941,14 @@ static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, 
   }
   const dim3 block(TILE_W, NWARPS);
   const dim3 grid(P.n_tiles + P.helper_cap);  // capacity of the work list; surplus CTAs exit at once
-  depth_filter_staged_kernel<PS><<<grid, block, smem, stream>>>(P, maps.maps);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = P.pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, depth_filter_staged_kernel<PS>, P, maps.maps);
 }
 
 cudaError_t launch_depth_filter_staged(const FilterParams &P, const StagedMaps &maps, int patch_side,

@@ -105,6 +105,7 @@ struct FilterParams
   int split_max;                         // most CTAs sharing one tile; 1 = never split
   int split_min_items, split_items_per_cta, sparse_max_seeds;  // tuning (staged_maps.cuh defaults)
   int heavy_min_items;                   // tiles with at least this many items are dispatched first
+  int pdl;                               // host only: launch with programmatic stream serialisation
   int split_avg_pct;                     // ... and split only above this percentage of the average items per CTA slot
   int cta_slots;                         // resident CTAs of the whole GPU (SMs x CTAs per SM)
   unsigned long long *tile_keys;         // [tiles][256] partial arg-max keys of split tiles

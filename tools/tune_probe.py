@@ -18,7 +18,7 @@ d_frames = torch.from_numpy(frames).to(dev)
 g = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera)); g.setStream(stream.cuda_stream); g.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED)
 
 def run(cfg):
-    for opt, val in zip((10, 11, 12, 13, 14, 15), cfg): g.setOption(opt, val)
+    for opt, val in zip((10, 11, 12, 13, 14, 15, 16), cfg): g.setOption(opt, val)
     best = 1e9; seg = None
     for rep in range(4):
         g.setReferenceImageDevice(d_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)
@@ -33,9 +33,8 @@ def run(cfg):
             best = tot; seg = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
     return best, seg
 
-for cfg in [(16, 512, 256, 16, 48, 100), (1, 512, 256, 16, 48, 100), (8, 512, 256, 16, 48, 100), (32, 512, 256, 16, 48, 100),
-            (16, 512, 256, 16, 48, 200), (16, 512, 256, 16, 48, 50), (16, 256, 256, 16, 48, 100), (16, 256, 128, 16, 48, 100),
-            (16, 384, 192, 16, 48, 100), (16, 512, 384, 16, 48, 100), (16, 512, 256, 8, 48, 100), (16, 512, 256, 16, 24, 100)]:
+for cfg in [(16, 512, 384, 16, 32, 100, 1), (16, 512, 384, 16, 32, 100, 2), (16, 512, 384, 16, 32, 100, 0), (16, 512, 256, 16, 48, 100, 1),
+            (16, 512, 384, 8, 32, 100, 2), (16, 512, 384, 12, 24, 100, 2), (16, 768, 384, 16, 32, 100, 2), (16, 512, 512, 16, 32, 100, 2)]:
     tot, seg = run(cfg)
-    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-199 %.2f ms" %
+    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d pdl %d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-199 %.2f ms" %
           (*cfg, tot, 199 / tot * 1e3, *seg))
