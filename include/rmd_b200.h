@@ -79,8 +79,9 @@ enum rmd_seeds_option {
    * off by default because nothing downstream of update() reads it
    * (it exists in the reference for tests: seed_matrix.cuh:76-83). */
   RMD_OPT_RECORD_MATCHES = 0,
-  /* 0: staged kernel (TMA -> shared memory, balanced candidate work list),
-   * 1: direct kernel (one thread per pixel, global loads); same arithmetic. */
+  /* 0 (default): staged kernel (TMA -> shared memory, balanced candidate work
+   * list), 1: direct kernel (one thread per pixel, global loads); same
+   * arithmetic, bit-identical results. */
   RMD_OPT_KERNEL_VARIANT = 1,
   /* fractional bits of the bilinear weights of the current-image taps
    * (8 = what the texture unit of the reference path uses; 0 = exact fp32). */
@@ -148,6 +149,27 @@ int rmd_seeds_update(rmd_seeds_t *s, const float *host_img,
                      const float *T_curr_world);
 int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img,
                         const float *T_curr_world);
+
+/* Frame ingest with lens undistortion.
+ * rmd::Depthmap::initUndistortionMap(k1, k2, r1, r2), src/depthmap.cpp:45-61:
+ * builds the fixed-point maps of cv::initUndistortRectifyMap(K, D, I, K, size,
+ * CV_16SC2) for the handle's camera.  From then on the *_u8 entry points
+ * (set_reference_u8, update_u8) run rmd::Depthmap::inputImage
+ * (src/depthmap.cpp:95-106) on the GPU, fused in one kernel: cv::remap(...,
+ * CV_INTER_LINEAR) of the 8-bit frame, then convertTo(CV_32F, 1/255.f).  Float
+ * entry points are not affected (the reference's SeedMatrix takes undistorted
+ * float images).  k1 = k2 = r1 = r2 = 0 is still a remap (identity up to the
+ * map's rounding); rmd_seeds_clear_undistortion_map() switches it off. */
+int rmd_seeds_init_undistortion_map(rmd_seeds_t *s, float k1, float k2, float r1, float r2);
+int rmd_seeds_clear_undistortion_map(rmd_seeds_t *s);
+/* The maps as OpenCV lays them out: xy = CV_16SC2 (2*w*h int16: x, y of the
+ * top-left source pixel), frac = CV_16UC1 (w*h: (fy << 5) | fx, 5-bit
+ * fractions).  Either pointer may be NULL. */
+int rmd_seeds_get_undistortion_map(rmd_seeds_t *s, int16_t *host_xy, uint16_t *host_frac);
+/* img_undistorted_8uc1_ of rmd::Depthmap (src/depthmap.cpp:99): the remapped
+ * 8-bit frame itself, host to host (the reference keeps it as the intensity
+ * source of the published point cloud).  Synchronous. */
+int rmd_seeds_undistort_u8(rmd_seeds_t *s, const uint8_t *host_src, uint8_t *host_dst);
 /* Frame already resident in device memory (must stay valid until the stream
  * has consumed it).  pitch_bytes must be a multiple of 16. */
 int rmd_seeds_update_device(rmd_seeds_t *s, const float *dev_img,

@@ -21,6 +21,7 @@
 #define RMD_ORACLE_H
 
 #include <stddef.h>
+#include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -107,6 +108,16 @@ void rmd_oracle_se3_inv(const float *T, float *out);
 void rmd_oracle_se3_mul(const float *A, const float *B, float *out);
 void rmd_oracle_se3_from_quat(float qw, float qx, float qy, float qz, float tx,
                               float ty, float tz, float *out);
+
+/* Frame ingest (rmd_oracle_ingest.c): rmd::Depthmap::initUndistortionMap and
+ * inputImage, src/depthmap.cpp:45-61,95-106 -- OpenCV's initUndistortRectifyMap
+ * (CV_16SC2 maps), remap (INTER_LINEAR, 8-bit) and convertTo(CV_32F, 1/255.f). */
+void rmd_oracle_undistort_maps(int width, int height, float fx, float fy, float cx,
+                               float cy, float k1, float k2, float p1, float p2,
+                               int16_t *map1, uint16_t *map2);
+void rmd_oracle_remap_u8(const uint8_t *src, int width, int height, const int16_t *map1,
+                         const uint16_t *map2, uint8_t *dst);
+void rmd_oracle_u8_to_float(const uint8_t *src, size_t n, float *dst);
 
 #ifdef __cplusplus
 }

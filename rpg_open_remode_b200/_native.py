@@ -46,6 +46,10 @@ _SIGNATURES = {
     "rmd_seeds_last_kernel_ms": (ci, [vp, P(cf)]),
     "rmd_seeds_enable_kernel_timing": (ci, [vp, ci]),
     "rmd_debug_host_profile": (ci, [P(ctypes.c_double), ci]),
+    "rmd_seeds_init_undistortion_map": (ci, [vp, cf, cf, cf, cf]),
+    "rmd_seeds_clear_undistortion_map": (ci, [vp]),
+    "rmd_seeds_get_undistortion_map": (ci, [vp, vp, vp]),
+    "rmd_seeds_undistort_u8": (ci, [vp, vp, vp]),
     "rmd_denoiser_create": (ci, [ci, ci, ci, P(vp)]),
     "rmd_denoiser_destroy": (ci, [vp]),
     "rmd_denoiser_set_stream": (ci, [vp, vp]),

@@ -309,6 +309,32 @@ class SeedMatrix:
               "SeedMatrix::setReferenceImageDevice")
         return True
 
+    # ---- frame ingest with lens undistortion (rmd::Depthmap::initUndistortionMap / inputImage,
+    # src/depthmap.cpp:45-61,95-106); applies to uint8 frames given to setReferenceImage / update
+    def initUndistortionMap(self, k1, k2, r1, r2) -> None:
+        check(self._L.rmd_seeds_init_undistortion_map(self._h, float(k1), float(k2), float(r1), float(r2)),
+              "SeedMatrix::initUndistortionMap")
+
+    def clearUndistortionMap(self) -> None:
+        check(self._L.rmd_seeds_clear_undistortion_map(self._h), "SeedMatrix::clearUndistortionMap")
+
+    def getUndistortionMap(self):
+        """(map1, map2) as cv::initUndistortRectifyMap(..., CV_16SC2) lays them out."""
+        m1 = np.empty((self.height_, self.width_, 2), np.int16)
+        m2 = np.empty((self.height_, self.width_), np.uint16)
+        check(self._L.rmd_seeds_get_undistortion_map(self._h, m1.ctypes.data, m2.ctypes.data),
+              "SeedMatrix::getUndistortionMap")
+        return m1, m2
+
+    def undistort(self, img_8uc1):
+        """The remapped 8-bit frame (img_undistorted_8uc1_ of rmd::Depthmap)."""
+        a = np.ascontiguousarray(img_8uc1, dtype=np.uint8)
+        if a.shape != (self.height_, self.width_):
+            raise ValueError("undistort: wrong shape")
+        out = np.empty_like(a)
+        check(self._L.rmd_seeds_undistort_u8(self._h, a.ctypes.data, out.ctypes.data), "SeedMatrix::undistort")
+        return out
+
     def uploadState(self, field: int, values) -> None:
         dt = np.int32 if field == FIELD_CONVERGENCE else np.float32
         a = np.ascontiguousarray(values, dtype=dt)
@@ -484,14 +510,16 @@ class Depthmap:
         self.is_distorted_ = False
 
     def initUndistortionMap(self, k1, k2, r1, r2):
-        raise NotImplementedError("lens undistortion (cv::remap) is host pre-processing outside the hot path "
-                                  "(SURVEY.md 8f row 1)")
+        """src/depthmap.cpp:45-61; the maps and the per-frame remap live on the GPU."""
+        self.seeds_.initUndistortionMap(k1, k2, r1, r2)
+        self.is_distorted_ = True
 
     def setReferenceImage(self, img_curr, T_curr_world, min_depth, max_depth) -> bool:
         self.denoiser_.setLargeSigmaSq(max_depth - min_depth)          # src/depthmap.cpp:69
         img = self._input_image(img_curr)
         ret = self.seeds_.setReferenceImage(img, T_curr_world, min_depth, max_depth)
-        self.ref_img_undistorted_8uc1_ = np.array(img, copy=True)
+        # img_undistorted_8uc1_.copyTo(ref_img_undistorted_8uc1_), src/depthmap.cpp:78
+        self.ref_img_undistorted_8uc1_ = self.seeds_.undistort(img) if self.is_distorted_ else np.array(img, copy=True)
         self.T_world_ref_ = (T_curr_world if isinstance(T_curr_world, SE3) else SE3(T_curr_world)).inv()
         return ret
 

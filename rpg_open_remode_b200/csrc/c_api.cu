@@ -18,6 +18,7 @@
 
 #include "denoiser.cuh"
 #include "host_copy.h"
+#include "ingest.cuh"
 #include "depth_filter.cuh"
 #include "reduction.cuh"
 #include "rmd_common.cuh"
@@ -169,6 +170,10 @@ struct rmd_seeds
   int tiles_x;
   int tune[7];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
+  // lens undistortion of 8-bit frames (ingest.cuh); maps are null until init_undistortion_map
+  short2 *undist_xy; uint16_t *undist_frac;
+  int16_t *undist_host_xy; uint16_t *undist_host_frac;
+  uint8_t *undist_tmp[2]; size_t undist_tmp_pitch;   // src / dst of rmd_seeds_undistort_u8
 };
 
 namespace
@@ -242,6 +247,8 @@ void seeds_free(rmd_seeds *s)
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
   delete s->copier;
+  cudaFree(s->undist_xy); cudaFree(s->undist_frac); cudaFree(s->undist_tmp[0]); cudaFree(s->undist_tmp[1]);
+  free(s->undist_host_xy); free(s->undist_host_frac);
   cudaGetLastError();
 }
 
@@ -390,6 +397,18 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   return 0;
 }
 
+// rmd::Depthmap::inputImage (src/depthmap.cpp:95-106) for a frame already on the
+// device: remap through the undistortion maps if the camera has them, then
+// 8U -> 32F * (1/255), in one kernel on the compute stream.
+cudaError_t u8_frame_to_float(rmd_seeds *s, const uint8_t *src, size_t src_pitch, float *dst, size_t dst_pitch)
+{
+  if(s->undist_xy)
+    return launch_undistort_u8(src, (int)src_pitch, s->undist_xy, s->undist_frac, dst,
+                               (int)(dst_pitch / sizeof(float)), NULL, 0, s->width, s->height, s->stream);
+  return launch_u8_to_float(src, (int)src_pitch, dst, (int)(dst_pitch / sizeof(float)), s->width, s->height,
+                            s->stream);
+}
+
 // Stage a host frame (float or u8) into the next ring slot and make the
 // compute stream wait for it.  Returns the slot.
 int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *slot_out)
@@ -437,9 +456,7 @@ int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *
   RMD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->copied[slot], 0));
   if(elem_size != sizeof(float))
   {
-    RMD_CUDA_TRY(launch_u8_to_float(s->curr_u8[slot], (int)s->curr_u8_pitch, s->curr[slot],
-                                    (int)(s->curr_pitch / sizeof(float)), s->width, s->height,
-                                    s->stream));
+    RMD_CUDA_TRY(u8_frame_to_float(s, s->curr_u8[slot], s->curr_u8_pitch, s->curr[slot], s->curr_pitch));
     s->n_total += 1;
   }
   s->slot_used[slot] = true;
@@ -517,7 +534,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[0] = staged::SPLIT_MAX; s->tune[1] = staged::SPLIT_MIN_ITEMS;
   s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
   s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT; s->tune[6] = 1;
-  s->variant = 1;
+  s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
   const int rc = seeds_alloc(s);
   if(rc)
   {
@@ -629,9 +646,7 @@ int rmd_seeds_set_reference_u8(rmd_seeds_t *s, const uint8_t *host_img, const fl
   RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
   RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr_u8[0], s->curr_u8_pitch, host_img, (size_t)s->width,
                                  (size_t)s->width, s->height, cudaMemcpyHostToDevice, s->stream));
-  RMD_CUDA_TRY(launch_u8_to_float(s->curr_u8[0], (int)s->curr_u8_pitch, s->ref,
-                                  (int)(s->ref_pitch / sizeof(float)), s->width, s->height,
-                                  s->stream));
+  RMD_CUDA_TRY(u8_frame_to_float(s, s->curr_u8[0], s->curr_u8_pitch, s->ref, s->ref_pitch));
   s->n_total += 1;
   return finish_set_reference(s, T_curr_world, min_depth, max_depth);
 }
@@ -667,6 +682,77 @@ int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_
   const int rc2 = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
   if(rc2) return rc2;
   RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
+  return 0;
+}
+
+int rmd_seeds_init_undistortion_map(rmd_seeds_t *s, float k1, float k2, float r1, float r2)
+{
+  RMD_REQUIRE(s, "rmd_seeds_init_undistortion_map: null handle");
+  DeviceGuard guard(s->device);
+  const size_t n = (size_t)s->width * s->height;
+  if(!s->undist_host_xy)
+  {
+    s->undist_host_xy = (int16_t*)malloc(n * 2 * sizeof(int16_t));
+    s->undist_host_frac = (uint16_t*)malloc(n * sizeof(uint16_t));
+    if(!s->undist_host_xy || !s->undist_host_frac)
+      return fail((int)cudaErrorMemoryAllocation, "rmd_seeds_init_undistortion_map: host allocation failed");
+  }
+  compute_undistort_maps(s->width, s->height, s->cam.fx, s->cam.fy, s->cam.cx, s->cam.cy, k1, k2, r1, r2,
+                         s->undist_host_xy, s->undist_host_frac);
+  short2 *xy = s->undist_xy;
+  uint16_t *frac = s->undist_frac;
+  if(!xy)
+  {
+    RMD_CUDA_TRY(cudaMalloc(&xy, n * sizeof(short2)));
+    RMD_CUDA_TRY(cudaMalloc(&frac, n * sizeof(uint16_t)));
+  }
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));   // frames in flight still use the previous maps
+  RMD_CUDA_TRY(cudaMemcpy(xy, s->undist_host_xy, n * sizeof(short2), cudaMemcpyHostToDevice));
+  RMD_CUDA_TRY(cudaMemcpy(frac, s->undist_host_frac, n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  s->undist_xy = xy;
+  s->undist_frac = frac;
+  return 0;
+}
+
+int rmd_seeds_clear_undistortion_map(rmd_seeds_t *s)
+{
+  RMD_REQUIRE(s, "rmd_seeds_clear_undistortion_map: null handle");
+  DeviceGuard guard(s->device);
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  cudaFree(s->undist_xy); cudaFree(s->undist_frac);
+  s->undist_xy = NULL; s->undist_frac = NULL;
+  return 0;
+}
+
+int rmd_seeds_get_undistortion_map(rmd_seeds_t *s, int16_t *host_xy, uint16_t *host_frac)
+{
+  RMD_REQUIRE(s, "rmd_seeds_get_undistortion_map: null handle");
+  if(!s->undist_xy)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_get_undistortion_map: init_undistortion_map has not been called");
+  const size_t n = (size_t)s->width * s->height;
+  if(host_xy) memcpy(host_xy, s->undist_host_xy, n * 2 * sizeof(int16_t));
+  if(host_frac) memcpy(host_frac, s->undist_host_frac, n * sizeof(uint16_t));
+  return 0;
+}
+
+int rmd_seeds_undistort_u8(rmd_seeds_t *s, const uint8_t *host_src, uint8_t *host_dst)
+{
+  RMD_REQUIRE(s && host_src && host_dst, "rmd_seeds_undistort_u8: null argument");
+  if(!s->undist_xy)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_undistort_u8: init_undistortion_map has not been called");
+  DeviceGuard guard(s->device);
+  for(int i = 0; i < 2; ++i)
+    if(!s->undist_tmp[i])
+      RMD_CUDA_TRY(cudaMallocPitch(&s->undist_tmp[i], &s->undist_tmp_pitch, (size_t)s->width, s->height));
+  RMD_CUDA_TRY(cudaMemcpy2DAsync(s->undist_tmp[0], s->undist_tmp_pitch, host_src, (size_t)s->width,
+                                 (size_t)s->width, s->height, cudaMemcpyHostToDevice, s->stream));
+  RMD_CUDA_TRY(launch_undistort_u8(s->undist_tmp[0], (int)s->undist_tmp_pitch, s->undist_xy, s->undist_frac,
+                                   NULL, 0, s->undist_tmp[1], (int)s->undist_tmp_pitch, s->width, s->height,
+                                   s->stream));
+  s->n_total += 1;
+  RMD_CUDA_TRY(cudaMemcpy2DAsync(host_dst, (size_t)s->width, s->undist_tmp[1], s->undist_tmp_pitch,
+                                 (size_t)s->width, s->height, cudaMemcpyDeviceToHost, s->stream));
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   return 0;
 }
 

@@ -65,6 +65,9 @@ def lib():
         L.rmd_oracle_se3_inv.argtypes = [vp, vp]
         L.rmd_oracle_se3_mul.argtypes = [vp, vp, vp]
         L.rmd_oracle_se3_from_quat.argtypes = [cf] * 7 + [vp]
+        L.rmd_oracle_undistort_maps.argtypes = [ci, ci, cf, cf, cf, cf, cf, cf, cf, cf, vp, vp]
+        L.rmd_oracle_remap_u8.argtypes = [vp, ci, ci, vp, vp, vp]
+        L.rmd_oracle_u8_to_float.argtypes = [vp, cs, vp]
         _lib = L
     return _lib
 
@@ -207,3 +210,28 @@ def set_threads(n):
 
 def get_threads():
     return lib().rmd_oracle_get_threads()
+
+
+# ---- frame ingest (oracle/rmd_oracle_ingest.c): src/depthmap.cpp:45-61,95-106
+def undistort_maps(width, height, fx, fy, cx, cy, k1, k2, p1, p2):
+    """(map1 int16 [h, w, 2], map2 uint16 [h, w]) of cv::initUndistortRectifyMap(..., CV_16SC2)."""
+    m1 = np.empty((height, width, 2), np.int16)
+    m2 = np.empty((height, width), np.uint16)
+    lib().rmd_oracle_undistort_maps(width, height, fx, fy, cx, cy, k1, k2, p1, p2, m1.ctypes.data, m2.ctypes.data)
+    return m1, m2
+
+
+def remap_u8(img, map1, map2):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    m1, m2 = np.ascontiguousarray(map1, np.int16), np.ascontiguousarray(map2, np.uint16)
+    out = np.empty_like(img)
+    lib().rmd_oracle_remap_u8(img.ctypes.data, w, h, m1.ctypes.data, m2.ctypes.data, out.ctypes.data)
+    return out
+
+
+def u8_to_float(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape, np.float32)
+    lib().rmd_oracle_u8_to_float(img.ctypes.data, img.size, out.ctypes.data)
+    return out

@@ -157,4 +157,55 @@ for label, src in (("e2e_float_frames_fps", frames), ("e2e_u8_frames_fps", u8)):
         best = dt if best is None else min(best, dt)
     out[label] = 199 / best
 
+# ingest with lens undistortion: the px4 launch-file camera, 752x480
+# (a) the whole 8-bit ingest chain of rmd::Depthmap::inputImage on the CPU with OpenCV, as the reference runs it;
+# (b) the same frame through the library: H2D of the 8-bit frame + one fused remap/convert kernel (+ D2H for the probe);
+# (c) VGA sequence end to end with distorted 8-bit frames in.
+try:
+    import cv2
+    Wd, Hd = 752, 480
+    camd = (418.715779404372, 418.186411716775, 397.573670639476, 246.235858293295)
+    distd = (-0.294854287021541, 0.0780596214365872, -0.000520874224877783, 9.42576963868232e-06)
+    K = np.array([[camd[0], 0, camd[2]], [0, camd[1], camd[3]], [0, 0, 1]], np.float32)
+    m1, m2 = cv2.initUndistortRectifyMap(K, np.array([distd], np.float32), np.eye(3), K, (Wd, Hd), cv2.CV_16SC2)
+    imgs = [rng.integers(0, 256, size=(Hd, Wd), dtype=np.uint8) for _ in range(50)]
+    cv2.setNumThreads(0)
+    t0 = time.perf_counter()
+    for k in range(200):
+        und = cv2.remap(imgs[k % 50], m1, m2, cv2.INTER_LINEAR)
+        flt = cv2.multiply(und, 1.0, scale=1.0 / 255.0, dtype=cv2.CV_32F)
+    out["ingest_752x480_opencv_cpu_1thread_us_per_frame"] = (time.perf_counter() - t0) / 200 * 1e6
+    gd = rmd.SeedMatrix(Wd, Hd, rmd.PinholeCamera(camd[0], camd[1], camd[2], camd[3]))
+    gd.initUndistortionMap(*distd)
+    got = gd.undistort(imgs[0])
+    out["ingest_752x480_matches_opencv"] = bool(np.array_equal(got, cv2.remap(imgs[0], m1, m2, cv2.INTER_LINEAR)))
+    t0 = time.perf_counter()
+    for k in range(200):
+        gd.undistort(imgs[k % 50])
+    out["ingest_752x480_library_h2d_kernel_d2h_sync_us_per_frame"] = (time.perf_counter() - t0) / 200 * 1e6
+    # device time of the fused remap+convert kernel: set_reference_u8 = H2D + that kernel + seed init; use CUDA events
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gd.setStream(stream.cuda_stream)
+    gd.setReferenceImage(imgs[0], poses[0], dmin, dmax)
+    for k in range(1, 4):
+        gd.update(imgs[k], poses[k])
+    gd.sync()
+except Exception as e:   # cv2 missing on the box: report it, do not fail the whole run
+    out["ingest_752x480_error"] = repr(e)
+
+# identity lens: the remap kernel runs, the frames (hence the filter work) stay the same
+g.initUndistortionMap(0.0, 0.0, 0.0, 0.0)
+best = None
+for rep in range(3):
+    g.setReferenceImage(u8[0], poses[0], dmin, dmax)
+    g.sync()
+    t0 = time.perf_counter()
+    for k in range(1, 200):
+        g.update(u8[k], poses[k])
+    g.sync()
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+out["e2e_u8_frames_with_undistortion_fps"] = 199 / best
+g.clearUndistortionMap()
+
 print(json.dumps(out, indent=1))
