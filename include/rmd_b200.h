@@ -221,6 +221,23 @@ int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on);
  * reset != 0 clears the accumulators after reading. */
 int rmd_debug_host_profile(double out[8], int reset);
 
+/* Point-cloud extraction.
+ * rmd::Publisher::publishPointCloud, src/publisher.cpp:54-86: every pixel whose
+ * state is CONVERGED becomes a point  T_world_ref * (normalize((x-cx)/fx,
+ * (y-cy)/fy, 1) * depth(y, x))  with the 8-bit intensity of the reference image,
+ * in row-major pixel order.  The reference downloads the depth and convergence
+ * maps and loops on the CPU; here the points are compacted on the device (same
+ * order, IEEE arithmetic in the reference's operation order) and only they are
+ * copied out.  `dev_depth` is a pitched device image (e.g. the denoised map of
+ * rmd_denoiser_run_seeds_to_device) or NULL for the seeds' own depth estimate.
+ * Points are 4 floats (x, y, z, intensity).  *count is always the number of
+ * CONVERGED pixels; at most `capacity_points` points are written.  Synchronous. */
+int rmd_seeds_point_cloud(rmd_seeds_t *s, const float *dev_depth, size_t depth_pitch_bytes,
+                          float *host_xyzi, size_t capacity_points, size_t *count);
+/* Same into device memory (16-byte aligned). */
+int rmd_seeds_point_cloud_device(rmd_seeds_t *s, const float *dev_depth, size_t depth_pitch_bytes,
+                                 float *dev_xyzi, size_t capacity_points, size_t *count);
+
 /* -------------------------------------------------------------- denoiser */
 
 /* DepthmapDenoiser(width, height), depthmap_denoiser.cu:143-177 */

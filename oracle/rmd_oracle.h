@@ -119,6 +119,13 @@ void rmd_oracle_remap_u8(const uint8_t *src, int width, int height, const int16_
                          const uint16_t *map2, uint8_t *dst);
 void rmd_oracle_u8_to_float(const uint8_t *src, size_t n, float *dst);
 
+/* Point cloud (rmd_oracle_pointcloud.c): rmd::Publisher::publishPointCloud,
+ * src/publisher.cpp:54-86 -- dense maps in, 4 floats per CONVERGED pixel out
+ * (NULL: count only); returns the number of points. */
+size_t rmd_oracle_point_cloud(const float *depth, const int *conv, const uint8_t *ref_u8,
+                              int width, int height, float fx, float fy, float cx, float cy,
+                              const float *T_world_ref, float *out);
+
 #ifdef __cplusplus
 }
 #endif

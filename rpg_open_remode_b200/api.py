@@ -335,6 +335,18 @@ class SeedMatrix:
         check(self._L.rmd_seeds_undistort_u8(self._h, a.ctypes.data, out.ctypes.data), "SeedMatrix::undistort")
         return out
 
+    def pointCloud(self, depth: "DeviceImage | None" = None, capacity: "int | None" = None):
+        """rmd::Publisher::publishPointCloud (src/publisher.cpp:54-86): float32 [n, 4] = (x, y, z, intensity) of the
+        CONVERGED pixels in row-major order, from the seeds' own depth or from a device depth image (e.g. denoised).
+        Returns (points, count); count > len(points) when `capacity` was too small."""
+        cap = self.width_ * self.height_ if capacity is None else int(capacity)
+        out = np.empty((cap, 4), np.float32)
+        n = ctypes.c_size_t()
+        ptr, pitch = (depth.data, depth.pitch) if depth is not None else (None, 0)
+        check(self._L.rmd_seeds_point_cloud(self._h, ptr, pitch, out.ctypes.data, cap, ctypes.byref(n)),
+              "SeedMatrix::pointCloud")
+        return out[:min(cap, n.value)], int(n.value)
+
     def uploadState(self, field: int, values) -> None:
         dt = np.int32 if field == FIELD_CONVERGENCE else np.float32
         a = np.ascontiguousarray(values, dtype=dt)

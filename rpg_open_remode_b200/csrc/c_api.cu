@@ -19,6 +19,7 @@
 #include "denoiser.cuh"
 #include "host_copy.h"
 #include "ingest.cuh"
+#include "point_cloud.cuh"
 #include "depth_filter.cuh"
 #include "reduction.cuh"
 #include "rmd_common.cuh"
@@ -174,6 +175,8 @@ struct rmd_seeds
   short2 *undist_xy; uint16_t *undist_frac;
   int16_t *undist_host_xy; uint16_t *undist_host_frac;
   uint8_t *undist_tmp[2]; size_t undist_tmp_pitch;   // src / dst of rmd_seeds_undistort_u8
+  // point-cloud extraction (point_cloud.cuh), allocated on first use
+  float4 *pc_points; unsigned int *pc_counts, *pc_total;
 };
 
 namespace
@@ -247,6 +250,7 @@ void seeds_free(rmd_seeds *s)
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
   delete s->copier;
+  cudaFree(s->pc_points); cudaFree(s->pc_counts); cudaFree(s->pc_total);
   cudaFree(s->undist_xy); cudaFree(s->undist_frac); cudaFree(s->undist_tmp[0]); cudaFree(s->undist_tmp[1]);
   free(s->undist_host_xy); free(s->undist_host_frac);
   cudaGetLastError();
@@ -754,6 +758,79 @@ int rmd_seeds_undistort_u8(rmd_seeds_t *s, const uint8_t *host_src, uint8_t *hos
                                  (size_t)s->width, s->height, cudaMemcpyDeviceToHost, s->stream));
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   return 0;
+}
+
+namespace
+{
+
+// Runs the two extraction kernels into `out` (device) and returns the number of CONVERGED pixels.
+int point_cloud_run(rmd_seeds *s, const float *dev_depth, size_t depth_pitch_bytes, float4 *out, size_t capacity,
+                    size_t *count)
+{
+  if(!s->has_reference)
+    return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_point_cloud: set_reference has not been called");
+  const int n_pixels = s->width * s->height;
+  PointCloudParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_blocks = (n_pixels + POINT_CLOUD_PIXELS - 1) / POINT_CLOUD_PIXELS;
+  if(!s->pc_counts)
+  {
+    RMD_CUDA_TRY(cudaMalloc(&s->pc_counts, sizeof(unsigned int) * (size_t)P.n_blocks));
+    RMD_CUDA_TRY(cudaMalloc(&s->pc_total, 2 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMemsetAsync(s->pc_total, 0, 2 * sizeof(unsigned int), s->stream));
+  }
+  P.width = s->width; P.height = s->height;
+  P.conv = s->conv; P.conv_stride = (int)(s->conv_pitch / sizeof(int));
+  if(dev_depth)
+  {
+    RMD_REQUIRE(depth_pitch_bytes >= sizeof(float) * (size_t)s->width && depth_pitch_bytes % sizeof(float) == 0,
+                "rmd_seeds_point_cloud: bad depth pitch");
+    P.depth = dev_depth; P.depth_stride = (int)(depth_pitch_bytes / sizeof(float)); P.depth_comps = 1;
+  }
+  else
+  {
+    P.depth = reinterpret_cast<const float*>(s->seed); P.depth_stride = s->seed_stride * 4; P.depth_comps = 4;  // mu
+  }
+  P.ref = s->ref; P.ref_stride = (int)(s->ref_pitch / sizeof(float));
+  P.cam = s->cam;
+  P.T_world_ref = s->T_world_ref;
+  P.out = out;
+  P.capacity = (unsigned int)(capacity > (size_t)n_pixels ? (size_t)n_pixels : capacity);
+  P.block_counts = s->pc_counts;
+  P.total = s->pc_total;
+  RMD_CUDA_TRY(launch_point_cloud(P, s->stream));
+  s->n_total += 2;
+  unsigned int n = 0;
+  RMD_CUDA_TRY(cudaMemcpyAsync(&n, s->pc_total, sizeof(n), cudaMemcpyDeviceToHost, s->stream));
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *count = n;
+  return 0;
+}
+
+} // namespace
+
+int rmd_seeds_point_cloud(rmd_seeds_t *s, const float *dev_depth, size_t depth_pitch_bytes,
+                          float *host_xyzi, size_t capacity_points, size_t *count)
+{
+  RMD_REQUIRE(s && count && (host_xyzi || capacity_points == 0), "rmd_seeds_point_cloud: null argument");
+  DeviceGuard guard(s->device);
+  if(!s->pc_points)
+    RMD_CUDA_TRY(cudaMalloc(&s->pc_points, sizeof(float4) * (size_t)s->width * s->height));
+  const int rc = point_cloud_run(s, dev_depth, depth_pitch_bytes, s->pc_points, (size_t)s->width * s->height, count);
+  if(rc) return rc;
+  const size_t n = *count < capacity_points ? *count : capacity_points;
+  if(n)
+    RMD_CUDA_TRY(cudaMemcpy(host_xyzi, s->pc_points, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int rmd_seeds_point_cloud_device(rmd_seeds_t *s, const float *dev_depth, size_t depth_pitch_bytes,
+                                 float *dev_xyzi, size_t capacity_points, size_t *count)
+{
+  RMD_REQUIRE(s && count && (dev_xyzi || capacity_points == 0), "rmd_seeds_point_cloud_device: null argument");
+  RMD_REQUIRE(((uintptr_t)dev_xyzi % 16) == 0, "rmd_seeds_point_cloud_device: output must be 16-byte aligned");
+  DeviceGuard guard(s->device);
+  return point_cloud_run(s, dev_depth, depth_pitch_bytes, reinterpret_cast<float4*>(dev_xyzi), capacity_points, count);
 }
 
 int rmd_seeds_update_device(rmd_seeds_t *s, const float *dev_img, size_t pitch_bytes,

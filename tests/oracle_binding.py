@@ -22,8 +22,8 @@ _lib = None
 
 
 def build_oracle(force: bool = False) -> str:
-    src = os.path.join(_ORACLE_DIR, "rmd_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_ORACLE_DIR, f) for f in os.listdir(_ORACLE_DIR) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _ORACLE_DIR, "cpu"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -68,6 +68,8 @@ def lib():
         L.rmd_oracle_undistort_maps.argtypes = [ci, ci, cf, cf, cf, cf, cf, cf, cf, cf, vp, vp]
         L.rmd_oracle_remap_u8.argtypes = [vp, ci, ci, vp, vp, vp]
         L.rmd_oracle_u8_to_float.argtypes = [vp, cs, vp]
+        L.rmd_oracle_point_cloud.argtypes = [vp, vp, vp, ci, ci, cf, cf, cf, cf, vp, vp]
+        L.rmd_oracle_point_cloud.restype = cs
         _lib = L
     return _lib
 
@@ -234,4 +236,20 @@ def u8_to_float(img):
     img = np.ascontiguousarray(img, np.uint8)
     out = np.empty(img.shape, np.float32)
     lib().rmd_oracle_u8_to_float(img.ctypes.data, img.size, out.ctypes.data)
+    return out
+
+
+# ---- point cloud (oracle/rmd_oracle_pointcloud.c): src/publisher.cpp:54-86
+def point_cloud(depth, conv, ref_u8, fx, fy, cx, cy, T_world_ref):
+    """float32 [n, 4] = (x, y, z, intensity) of the CONVERGED pixels, row-major order."""
+    depth = np.ascontiguousarray(depth, np.float32)
+    conv = np.ascontiguousarray(conv, np.int32)
+    ref_u8 = np.ascontiguousarray(ref_u8, np.uint8)
+    h, w = depth.shape
+    T = np.ascontiguousarray(np.asarray(T_world_ref, np.float32).reshape(-1)[:12])
+    n = lib().rmd_oracle_point_cloud(depth.ctypes.data, conv.ctypes.data, ref_u8.ctypes.data, w, h, fx, fy, cx, cy,
+                                     T.ctypes.data, None)
+    out = np.empty((n, 4), np.float32)
+    lib().rmd_oracle_point_cloud(depth.ctypes.data, conv.ctypes.data, ref_u8.ctypes.data, w, h, fx, fy, cx, cy,
+                                 T.ctypes.data, out.ctypes.data)
     return out

@@ -208,4 +208,30 @@ for rep in range(3):
 out["e2e_u8_frames_with_undistortion_fps"] = 199 / best
 g.clearUndistortionMap()
 
+# point cloud: VGA keyframe after 199 updates
+import oracle_binding as ob  # noqa: E402  (the reference's CPU loop, transcribed: the baseline of this row)
+g.setReferenceImage(u8[0], poses[0], dmin, dmax)
+for k in range(1, 200):
+    g.update(u8[k], poses[k])
+g.sync()
+pts, n_pts = g.pointCloud()
+t0 = time.perf_counter()
+for _ in range(20):
+    pts, n_pts = g.pointCloud()
+out["point_cloud_vga_points"] = int(n_pts)
+out["point_cloud_vga_library_ms_incl_d2h_of_points"] = (time.perf_counter() - t0) / 20 * 1e3
+t0 = time.perf_counter()
+for _ in range(20):
+    mu, conv = g.downloadDepthmap(), g.downloadConvergence()
+t_dl = (time.perf_counter() - t0) / 20
+T_world_ref = ob.se3_inv(poses[0].reshape(3, 4))
+camf = [float(np.float32(c)) for c in seq.camera]
+t0 = time.perf_counter()
+for _ in range(5):
+    ref_pts = ob.point_cloud(mu, conv, u8[0], *camf, T_world_ref)
+t_cpu = (time.perf_counter() - t0) / 5
+out["point_cloud_vga_reference_way_ms"] = {"download_depth_and_convergence": t_dl * 1e3,
+                                            "cpu_loop_two_passes_count_then_fill": t_cpu * 1e3}
+out["point_cloud_vga_matches_cpu_loop"] = bool(np.array_equal(pts, ref_pts))
+
 print(json.dumps(out, indent=1))

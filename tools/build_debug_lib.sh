@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 mkdir -p tools/build/dbg
 SRC=rpg_open_remode_b200/csrc
 FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -use_fast_math -Xcompiler -fPIC -DRMD_DEBUG_COUNTERS=1"
-for f in c_api depth_filter depth_filter_staged denoiser reduction ingest; do
+for f in c_api depth_filter depth_filter_staged denoiser reduction ingest point_cloud; do
   nvcc $FLAGS -c $SRC/$f.cu -o tools/build/dbg/$f.o &
 done
 wait
