@@ -235,14 +235,14 @@ def run_ours(args, rank, world, local_rank):
     host_frames = torch.from_numpy(frames).pin_memory()
     dev_frames = host_frames.to(dev, non_blocking=False)
     frame_bytes = W * H * 4
-    depth_out = torch.empty((H, W), dtype=torch.float32, device=dev)
-    conv_out = torch.empty((H, W), dtype=torch.int32, device=dev)
+    gatherer = multi_gpu.MapGatherer(H, W, dev, dst=0)    # depth + convergence in one buffer: one collective per step
+    depth_out, conv_out = gatherer.depth, gatherer.convergence
 
     def final_gather():
         # the only collective on the path: final depth + convergence maps to rank 0 (NCCL)
         seeds.copyFieldToDevice(rmd.FIELD_MU, depth_out.data_ptr(), W * 4)
         seeds.copyFieldToDevice(rmd.FIELD_CONVERGENCE, conv_out.data_ptr(), W * 4)
-        return multi_gpu.gather_maps(depth_out, conv_out, dst=0)
+        return gatherer.gather()
 
     def step_resident():
         seeds.setReferenceImageDevice(dev_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)

@@ -50,6 +50,36 @@ def gather_maps(depth: torch.Tensor, convergence: torch.Tensor, dst: int = 0
     return (depths, convs) if rank == dst else None
 
 
+class MapGatherer:
+    """The same final gather as gather_maps() for a loop: depth (f32) and convergence (i32)
+    live in ONE preallocated buffer per rank, so a round is a single collective with no
+    allocation -- at VGA the two-collective version cost ~1 ms per keyframe on 2 B200s,
+    an eighth of the keyframe itself.
+
+        g = MapGatherer(height, width, device)
+        ... write the final maps into g.depth / g.convergence (views of g.packed) ...
+        out = g.gather()      # on dst: ([depth of rank 0, ...], [convergence of rank 0, ...]); None elsewhere
+    """
+
+    def __init__(self, height: int, width: int, device=None, dst: int = 0):
+        self.packed = torch.empty((2, height, width), dtype=torch.int32, device=device)
+        self.depth = self.packed[0].view(torch.float32)
+        self.convergence = self.packed[1]
+        self.dst = dst
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.recv = None
+        if self.active and dist.get_rank() == dst:
+            self.recv = [torch.empty_like(self.packed) for _ in range(dist.get_world_size())]
+
+    def gather(self) -> Optional[Tuple[List[torch.Tensor], List[torch.Tensor]]]:
+        if not self.active:
+            return [self.depth], [self.convergence]
+        dist.gather(self.packed, self.recv, dst=self.dst)
+        if self.recv is None:
+            return None
+        return [r[0].view(torch.float32) for r in self.recv], [r[1] for r in self.recv]
+
+
 def max_over_ranks(value: float, device: Optional[torch.device] = None) -> float:
     """Timing convention: a multi-GPU duration is the max over ranks."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -60,6 +60,19 @@ def _worker(rank, world, port, n_keyframes, out_dir):
                     results[k] = (v.numpy(), multi_gpu.assemble(round_kfs, convs)[k].numpy())
             else:
                 assert got is None
+        # the single-collective gatherer of the bench loop gives the same maps
+        mu, conv = _keyframe_maps(mine[0])
+        mg = multi_gpu.MapGatherer(mu.shape[0], mu.shape[1])
+        for _ in range(2):   # reusable
+            mg.depth.copy_(torch.from_numpy(mu))
+            mg.convergence.copy_(torch.from_numpy(conv))
+            got = mg.gather()
+            if rank == 0:
+                for r in range(world):
+                    mu_r, conv_r = _keyframe_maps(shards[r][0])
+                    assert np.array_equal(got[0][r].numpy(), mu_r) and np.array_equal(got[1][r].numpy(), conv_r)
+            else:
+                assert got is None
         t = multi_gpu.max_over_ranks(float(rank + 1))
         assert t == float(world)
         if rank == 0:
@@ -101,3 +114,9 @@ def test_gather_without_process_group():
     depths, convs = multi_gpu.gather_maps(d, c)
     assert depths[0] is d and convs[0] is c
     assert multi_gpu.max_over_ranks(1.5) == 1.5
+    mg = multi_gpu.MapGatherer(4, 5)
+    mg.depth.fill_(1.25)
+    mg.convergence.fill_(3)
+    depths, convs = mg.gather()
+    assert depths[0].dtype == torch.float32 and float(depths[0][2, 2]) == 1.25 and int(convs[0][3, 4]) == 3
+    assert depths[0].data_ptr() == mg.packed.data_ptr()      # views of the one buffer: no copy
