@@ -150,6 +150,19 @@ int rmd_seeds_update(rmd_seeds_t *s, const float *host_img,
 int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img,
                         const float *T_curr_world);
 
+/* Several live reference keyframes against one incoming frame (SURVEY.md 8f
+ * row 2; the reference node keeps a single rmd::Depthmap and re-keyframes,
+ * src/depthmap_node.cpp:125-157).  The frame is staged and uploaded ONCE
+ * (through handles[0]) and every handle's fused kernel is enqueued on its own
+ * stream, so the kernels of different keyframes overlap on the GPU -- steady
+ * frames of one keyframe leave most issue slots idle.  Same
+ * result as calling rmd_seeds_update[_u8] on each handle.  All handles must
+ * have the same image size and device and a reference frame. */
+int rmd_seeds_update_many(rmd_seeds_t *const *handles, int n, const float *host_img,
+                          const float *T_curr_world);
+int rmd_seeds_update_many_u8(rmd_seeds_t *const *handles, int n, const uint8_t *host_img,
+                             const float *T_curr_world);
+
 /* Frame ingest with lens undistortion.
  * rmd::Depthmap::initUndistortionMap(k1, k2, r1, r2), src/depthmap.cpp:45-61:
  * builds the fixed-point maps of cv::initUndistortRectifyMap(K, D, I, K, size,

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "rmd_seeds_clear_undistortion_map": (ci, [vp]),
     "rmd_seeds_get_undistortion_map": (ci, [vp, vp, vp]),
     "rmd_seeds_undistort_u8": (ci, [vp, vp, vp]),
+    "rmd_seeds_update_many": (ci, [P(vp), ci, vp, vp]),
+    "rmd_seeds_update_many_u8": (ci, [P(vp), ci, vp, vp]),
     "rmd_seeds_point_cloud": (ci, [vp, vp, cs, vp, cs, P(cs)]),
     "rmd_seeds_point_cloud_device": (ci, [vp, vp, cs, vp, cs, P(cs)]),
     "rmd_denoiser_create": (ci, [ci, ci, ci, P(vp)]),

@@ -335,6 +335,21 @@ class SeedMatrix:
         check(self._L.rmd_seeds_undistort_u8(self._h, a.ctypes.data, out.ctypes.data), "SeedMatrix::undistort")
         return out
 
+    @staticmethod
+    def updateMany(seeds: "list[SeedMatrix]", host_curr_img_align_row_maj, T_curr_world) -> bool:
+        """Several live keyframes against one incoming frame (rmd_seeds_update_many): one upload, one fused kernel
+        per keyframe on its own stream.  Same result as update() on each; an 8-bit frame goes through seeds[0]'s
+        ingest (undistortion map)."""
+        if not seeds:
+            raise ValueError("updateMany: no keyframes")
+        first = seeds[0]
+        img = first._frame(host_curr_img_align_row_maj)
+        T = _pose12(T_curr_world)
+        arr = (ctypes.c_void_p * len(seeds))(*[s._h.value for s in seeds])
+        fn = first._L.rmd_seeds_update_many_u8 if img.dtype == np.uint8 else first._L.rmd_seeds_update_many
+        check(fn(arr, len(seeds), img.ctypes.data, T.ctypes.data), "SeedMatrix::updateMany")
+        return True
+
     def pointCloud(self, depth: "DeviceImage | None" = None, capacity: "int | None" = None):
         """rmd::Publisher::publishPointCloud (src/publisher.cpp:54-86): float32 [n, 4] = (x, y, z, intensity) of the
         CONVERGED pixels in row-major order, from the seeds' own depth or from a device depth image (e.g. denoised).

@@ -175,6 +175,7 @@ struct rmd_seeds
   short2 *undist_xy; uint16_t *undist_frac;
   int16_t *undist_host_xy; uint16_t *undist_host_frac;
   uint8_t *undist_tmp[2]; size_t undist_tmp_pitch;   // src / dst of rmd_seeds_undistort_u8
+  cudaEvent_t fan_ev;   // rmd_seeds_update_many: frame ready (handles[0]) / update enqueued (the others)
   // point-cloud extraction (point_cloud.cuh), allocated on first use
   float4 *pc_points; unsigned int *pc_counts, *pc_total;
 };
@@ -251,6 +252,7 @@ void seeds_free(rmd_seeds *s)
   delete s->maps;
   delete s->copier;
   cudaFree(s->pc_points); cudaFree(s->pc_counts); cudaFree(s->pc_total);
+  if(s->fan_ev) cudaEventDestroy(s->fan_ev);
   cudaFree(s->undist_xy); cudaFree(s->undist_frac); cudaFree(s->undist_tmp[0]); cudaFree(s->undist_tmp[1]);
   free(s->undist_host_xy); free(s->undist_host_frac);
   cudaGetLastError();
@@ -687,6 +689,62 @@ int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_
   if(rc2) return rc2;
   RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
   return 0;
+}
+
+namespace
+{
+
+int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t elem_size, const float *T_curr_world)
+{
+  RMD_REQUIRE(handles && n >= 1 && host_img && T_curr_world, "rmd_seeds_update_many: null argument");
+  rmd_seeds *h0 = handles[0];
+  for(int i = 0; i < n; ++i)
+  {
+    rmd_seeds *h = handles[i];
+    RMD_REQUIRE(h, "rmd_seeds_update_many: null handle");
+    if(!h->has_reference)
+      return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_many: a handle has no reference frame");
+    RMD_REQUIRE(h->width == h0->width && h->height == h0->height && h->device == h0->device,
+                "rmd_seeds_update_many: handles differ in image size or device");
+    for(int j = 0; j < i; ++j)
+      RMD_REQUIRE(handles[j] != h, "rmd_seeds_update_many: the same handle twice");
+  }
+  ProfScope prof(5);
+  if(g_prof_on) g_prof[6] += 1.0;
+  DeviceGuard guard(h0->device);
+  for(int i = 0; i < n; ++i)
+    if(!handles[i]->fan_ev)
+      RMD_CUDA_TRY(cudaEventCreateWithFlags(&handles[i]->fan_ev, cudaEventDisableTiming));
+  int slot = 0;
+  const int rc = stage_host_frame(h0, host_img, elem_size, &slot);   // one pinned copy, one upload (+ ingest kernel)
+  if(rc) return rc;
+  RMD_CUDA_TRY(cudaEventRecord(h0->fan_ev, h0->stream));            // the float frame is ready
+  for(int i = 1; i < n; ++i)
+  {
+    rmd_seeds *h = handles[i];
+    RMD_CUDA_TRY(cudaStreamWaitEvent(h->stream, h0->fan_ev, 0));
+    const int rci = enqueue_update(h, h0->curr[slot], h0->curr_pitch, T_curr_world);
+    if(rci) return rci;
+    RMD_CUDA_TRY(cudaEventRecord(h->fan_ev, h->stream));
+  }
+  const int rc0 = enqueue_update(h0, h0->curr[slot], h0->curr_pitch, T_curr_world);
+  if(rc0) return rc0;
+  for(int i = 1; i < n; ++i)
+    RMD_CUDA_TRY(cudaStreamWaitEvent(h0->stream, handles[i]->fan_ev, 0));   // the slot is free when ALL have read it
+  RMD_CUDA_TRY(cudaEventRecord(h0->consumed[slot], h0->stream));
+  return 0;
+}
+
+} // namespace
+
+int rmd_seeds_update_many(rmd_seeds_t *const *handles, int n, const float *host_img, const float *T_curr_world)
+{
+  return update_many(handles, n, host_img, sizeof(float), T_curr_world);
+}
+
+int rmd_seeds_update_many_u8(rmd_seeds_t *const *handles, int n, const uint8_t *host_img, const float *T_curr_world)
+{
+  return update_many(handles, n, host_img, sizeof(uint8_t), T_curr_world);
 }
 
 int rmd_seeds_init_undistortion_map(rmd_seeds_t *s, float k1, float k2, float r1, float r2)
