@@ -485,8 +485,9 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     // slot's worth of items each (never fewer than split_items_per_cta, the fixed
     // cost of a CTA must pay off), so the frame's CTAs finish together and the sum
     // of all helpers stays below the number of slots.
+    // (no estimate of the frame's total in the first frame of a keyframe: no split)
     int znext = 1;
-    if(P.split_max > 1 && items > P.split_min_items)
+    if(P.split_max > 1 && items > P.split_min_items && P.counts_cur[3] != 0u)
     {
       const unsigned int target = max((unsigned int)P.split_items_per_cta, avg_per_slot * (unsigned int)P.split_avg_pct / 100u);
       znext = (int)min((unsigned int)P.split_max, ((unsigned int)items + target - 1u) / target);
