@@ -89,6 +89,30 @@ def test_identity_lens_and_float_conversion_properties():
     assert np.all(np.diff(f.ravel()) > 0) and np.array_equal(np.rint(f * 255).astype(np.uint8), ramp)
 
 
+def test_oracle_matches_live_opencv_on_random_cameras():
+    """Beyond the committed fixtures: wherever cv2 is importable (it is in this image), 40 seeded random
+    cameras / lenses / sizes, maps + remap + conversion, all bit-exact."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(20260923)
+    for case in range(40):
+        w, h = int(rng.integers(24, 200)), int(rng.integers(24, 160))
+        fx, fy = float(rng.uniform(0.5, 2.0) * w), float(rng.choice([-1, 1]) * rng.uniform(0.5, 2.0) * w)
+        cx, cy = float(rng.uniform(0.3, 0.7) * w), float(rng.uniform(0.3, 0.7) * h)
+        dist = [float(rng.uniform(-0.4, 0.4)), float(rng.uniform(-0.15, 0.15)), float(rng.uniform(-0.01, 0.01)),
+                float(rng.uniform(-0.01, 0.01))]
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+        D = np.array([dist], np.float32)
+        m1, m2 = cv2.initUndistortRectifyMap(K, D, np.eye(3), K, (w, h), cv2.CV_16SC2)
+        cam = [float(v) for v in (K[0, 0], K[1, 1], K[0, 2], K[1, 2])]
+        o1, o2 = ob.undistort_maps(w, h, *cam, *[float(v) for v in D[0]])
+        assert np.array_equal(o1, m1) and np.array_equal(o2, m2), f"case {case}: maps differ"
+        img = texture(w, h, case)
+        und = cv2.remap(img, m1, m2, cv2.INTER_LINEAR)
+        assert np.array_equal(ob.remap_u8(img, o1, o2), und), f"case {case}: remap differs"
+        flt = cv2.multiply(und, 1.0, scale=float(np.float32(1.0) / np.float32(255.0)), dtype=cv2.CV_32F)
+        assert np.array_equal(ob.u8_to_float(und), flt), f"case {case}: conversion differs"
+
+
 # ------------------------------------------------------------------ GPU: the product
 gpu = pytest.mark.gpu
 
