@@ -15,14 +15,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "undistort_maps.h"   // compute_undistort_maps(): host, once per camera
+
 namespace rmdb
 {
-
-// Fixed-point undistortion maps as OpenCV's CV_16SC2 / CV_16UC1 pair: xy[i] =
-// integer source pixel, frac[i] = (fy << 5) | fx with 5-bit fractions.  Pure
-// host computation in double precision, once per camera.
-void compute_undistort_maps(int width, int height, float fx, float fy, float cx, float cy,
-                            float k1, float k2, float p1, float p2, int16_t *xy, uint16_t *frac);
 
 // One pass over the frame: bilinear remap of the 8-bit source through the maps
 // (constant 0 outside the image, 15-bit fixed-point weights, round to nearest

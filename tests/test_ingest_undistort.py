@@ -113,6 +113,51 @@ def test_oracle_matches_live_opencv_on_random_cameras():
         assert np.array_equal(ob.u8_to_float(und), flt), f"case {case}: conversion differs"
 
 
+def _product_maps_fn():
+    """The product's own host code (csrc/undistort_maps.h), built into a shim with the system compiler the same way
+    nvcc hands it to the host compiler (-O3, no fast-math)."""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "tests", "cpp", "build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libundistort_maps_shim.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++14", "-O3", "-fPIC", "-shared", os.path.join(root, "tests", "cpp", "undistort_maps_shim.cpp"),
+                           "-o", lib])
+    L = ctypes.CDLL(lib)
+    L.product_undistort_maps.argtypes = [ctypes.c_int] * 2 + [ctypes.c_float] * 8 + [ctypes.c_void_p] * 2
+
+    def maps(w, h, fx, fy, cx, cy, k1, k2, p1, p2):
+        m1, m2 = np.empty((h, w, 2), np.int16), np.empty((h, w), np.uint16)
+        L.product_undistort_maps(w, h, fx, fy, cx, cy, k1, k2, p1, p2, m1.ctypes.data, m2.ctypes.data)
+        return m1, m2
+    return maps
+
+
+def test_product_host_map_code_matches_opencv(gold):
+    """Not only the oracle: the product's host-side map computation itself, on the CPU, against the golden vectors
+    (three cameras incl. launch/px4_2.launch at 752x480) and, where cv2 is importable, 40 random cameras."""
+    maps = _product_maps_fn()
+    for name in ("small", "tilt"):
+        w, h, cam, dist = _cam(gold, name)
+        m1, m2 = maps(w, h, *cam, *dist)
+        assert np.array_equal(m1, gold[f"{name}_map1"]) and np.array_equal(m2, gold[f"{name}_map2"]), name
+    w, h, cam, dist = _cam(gold, "px4")
+    m1, m2 = maps(w, h, *cam, *dist)
+    assert sha(m1) == str(gold["px4_map1_sha256"]) and sha(m2) == str(gold["px4_map2_sha256"])
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    for case in range(40):
+        w, h = int(rng.integers(24, 260)), int(rng.integers(24, 200))
+        K = np.array([[rng.uniform(0.5, 2.0) * w, 0, rng.uniform(0.3, 0.7) * w],
+                      [0, rng.choice([-1, 1]) * rng.uniform(0.5, 2.0) * w, rng.uniform(0.3, 0.7) * h], [0, 0, 1]], np.float32)
+        D = np.array([[rng.uniform(-0.4, 0.4), rng.uniform(-0.15, 0.15), rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01)]], np.float32)
+        c1, c2 = cv2.initUndistortRectifyMap(K, D, np.eye(3), K, (w, h), cv2.CV_16SC2)
+        m1, m2 = maps(w, h, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), *[float(v) for v in D[0]])
+        assert np.array_equal(m1, c1) and np.array_equal(m2, c2), f"case {case}"
+
+
 # ------------------------------------------------------------------ GPU: the product
 gpu = pytest.mark.gpu
 
