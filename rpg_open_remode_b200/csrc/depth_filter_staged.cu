@@ -942,8 +942,7 @@ static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, 
   }
   const dim3 block(TILE_W, NWARPS);
   const dim3 grid(P.n_tiles + P.helper_cap);  // capacity of the work list; surplus CTAs exit at once
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
