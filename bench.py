@@ -186,6 +186,22 @@ def ncu_traffic():
         return None
 
 
+def ncu_issue_utilisation():
+    """The bound that actually applies: issue-slot utilisation of the dominant kernel in a
+    search-heavy and in a steady frame, from the same committed ncu capture; None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_staged.json")) as f:
+            m = json.load(f)["metrics"]
+        key = "smsp__issue_active.avg.pct_of_peak_sustained_active"
+        return {"bound": "instruction issue (search-heavy frames) / dependent-chain latency (steady frames)",
+                "heavy_frame_issue_slots_pct": float(m[key]["heavy"]), "steady_frame_issue_slots_pct": float(m[key]["steady"]),
+                "heavy_frame_us_under_ncu": float(m["gpu__time_duration.sum"]["heavy"]),
+                "steady_frame_us_under_ncu": float(m["gpu__time_duration.sum"]["steady"]),
+                "source": "profiles/r01_ncu_staged.md"}
+    except Exception:
+        return None
+
+
 def cpu_baseline(args, frames, poses, dmin, dmax, seq):
     """CPU oracle port (oracle/librmd_oracle.so, OpenMP, all host threads) timed
     on a bounded sample of the same workload: frames 1..n of the sequence."""
@@ -320,6 +336,7 @@ def run_ours(args, rank, world, local_rank):
                                           float(per_launch_ms.max() * 1e3)],
                     "sum_over_step": float(per_launch_ms.sum() / ms_per_step)},
                 "kernel_share_of_step": ncu_kernel_share(),
+                "what_bounds_it": ncu_issue_utilisation(),
                 "note": "search-heavy frames are instruction-issue bound (<=143 candidates x 25 bilinear taps per "
                         "seed), steady frames latency bound; not HBM bound: see DESIGN.md 4.1 'What bounds it'"}
 
