@@ -2,7 +2,7 @@
 (ours / CPU oracle / the reference's rebuilt CUDA kernels) so the tolerances in
 tests/ are set from data, and times both CUDA paths per frame.
 
-    python tools/gpu_diag.py [--width 320 --height 240 --frames 30] > gpurun_out/diag.txt
+    python tests/perf/gpu_diag.py [--width 320 --height 240 --frames 30] > gpurun_out/diag.txt
 """
 import argparse
 import json
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

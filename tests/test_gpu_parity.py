@@ -6,7 +6,7 @@ triangulation uncertainty (src/triangulation.cu:53-68: z_plus - z cancels 3-4
 digits, so approximate sin/div move tau by ~1e-3 relative), which feeds sigma^2.
 Tolerances below were set from the spread MEASURED on a B200 between the oracle
 and the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref):
-tools/gpu_diag.py, profiles/r01_parity_spread.md.  They are the same spread:
+tests/perf/gpu_diag.py, profiles/r01_parity_spread.md.  They are the same spread:
 our kernels agree with the reference's CUDA build far more tightly (see
 test_ref_cuda_parity.py), so what is bounded here is IEEE-vs-fast-math.
 
