@@ -93,12 +93,12 @@ enum rmd_seeds_option {
   RMD_OPT_DEBUG_TIMELINE = 3,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */
-  RMD_OPT_TUNE_SPLIT_MAX = 10,
-  RMD_OPT_TUNE_SPLIT_MIN_ITEMS = 11,
-  RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA = 12,
-  RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13,
-  RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14,
-  RMD_OPT_TUNE_SPLIT_AVG_PCT = 15,
+  RMD_OPT_TUNE_SPLIT_MAX = 10,            /* most CTAs sharing one busy tile (1 = never split; default 16) */
+  RMD_OPT_TUNE_SPLIT_MIN_ITEMS = 11,      /* tiles with fewer work items are never split (512) */
+  RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA = 12,  /* least work items a CTA of a split tile gets (384) */
+  RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13,     /* tiles with at most this many seeds to update skip TMA staging (16; 0 = off) */
+  RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14,      /* tiles with at least this many items are dispatched first (32) */
+  RMD_OPT_TUNE_SPLIT_AVG_PCT = 15,        /* target items per CTA of a split tile, in % of the frame's items per resident CTA slot (100) */
   RMD_OPT_TUNE_PDL = 16            /* 1 (default): programmatic dependent launch of consecutive frames */
 };
 
