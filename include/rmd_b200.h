@@ -91,6 +91,15 @@ enum rmd_seeds_option {
    * with rmd_seeds_download(h, RMD_FIELD_DEBUG_TIMELINE, dst) where dst holds
    * 16 * ceil(w/32) * ceil(h/8) int64 values. */
   RMD_OPT_DEBUG_TIMELINE = 3,
+  /* 1: a host frame given to rmd_seeds_update* / set_reference* that lies in
+   * page-locked memory (cudaHostAlloc / cudaHostRegister, detected with
+   * cudaPointerGetAttributes) is DMA'd straight from the caller's buffer:
+   * no staging copy into the library's pinned ring.  The caller then must
+   * leave the frame untouched until rmd_seeds_sync() (or any download)
+   * returns -- the reference's "reusable on return" guarantee
+   * (device_image.cuh:93-106) no longer holds for such buffers.  Pageable
+   * buffers still take the staged path.  Default 0. */
+  RMD_OPT_PINNED_INPUT = 4,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */
   RMD_OPT_TUNE_SPLIT_MAX = 10,            /* most CTAs sharing one busy tile (1 = never split; default 16) */
@@ -209,7 +218,9 @@ int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src);
  * device image of the field, valid until the next call on this handle. */
 int rmd_seeds_device_ptr(rmd_seeds_t *s, int field, void **dev_ptr,
                          size_t *pitch_bytes);
-/* Copy a field into caller-owned device memory on the handle's stream. */
+/* Copy a field into caller-owned device memory, ASYNCHRONOUSLY on the handle's
+ * stream: a consumer on any other stream (including the legacy default stream
+ * of rmd_reduce_* and the denoiser's own stream) must rmd_seeds_sync() first. */
 int rmd_seeds_copy_field_to_device(rmd_seeds_t *s, int field, void *dev_dst,
                                    size_t dst_pitch_bytes);
 
@@ -272,7 +283,11 @@ int rmd_denoiser_run(rmd_denoiser_t *d, const float *mu, size_t mu_pitch,
 /* Same, reading the seed state of `s` directly (no planar export). */
 int rmd_denoiser_run_seeds(rmd_denoiser_t *d, rmd_seeds_t *s,
                            float *host_denoised, float lambda, int iterations);
-/* Same, leaving the result in caller-owned device memory (no D2H copy). */
+/* Same, leaving the result in caller-owned device memory (no D2H copy).
+ * Asynchronous on the denoiser's stream.  The seeds handle is ordered after it:
+ * a following rmd_seeds_point_cloud(s, dev_out, ...), update or set_reference
+ * on `s` waits (on the device) for the denoised map / for the read of the seed
+ * state.  Any OTHER consumer of dev_out must rmd_denoiser_sync() first. */
 int rmd_denoiser_run_seeds_to_device(rmd_denoiser_t *d, rmd_seeds_t *s,
                                      float *dev_out, size_t out_pitch_bytes,
                                      float lambda, int iterations);

@@ -176,6 +176,11 @@ struct rmd_seeds
   int16_t *undist_host_xy; uint16_t *undist_host_frac;
   uint8_t *undist_tmp[2]; size_t undist_tmp_pitch;   // src / dst of rmd_seeds_undistort_u8
   cudaEvent_t fan_ev;   // rmd_seeds_update_many: frame ready (handles[0]) / update enqueued (the others)
+  bool pinned_input;    // RMD_OPT_PINNED_INPUT
+  uint8_t *ref_u8; size_t ref_u8_pitch;   // scratch of rmd_seeds_set_reference_u8 (not a ring slot)
+  // Work another handle (the denoiser) enqueued on ITS stream against this handle's buffers: the
+  // next operation on s->stream that touches them waits for ext_ev first.
+  cudaEvent_t ext_ev; bool ext_pending;
   // point-cloud extraction (point_cloud.cuh), allocated on first use
   float4 *pc_points; unsigned int *pc_counts, *pc_total;
 };
@@ -202,6 +207,7 @@ int seeds_alloc(rmd_seeds *s)
     RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
     RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
   }
+  RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->ext_ev, cudaEventDisableTiming));
   RMD_CUDA_TRY(cudaMalloc(&s->counters, 3 * sizeof(unsigned int)));
   RMD_CUDA_TRY(cudaMemset(s->counters, 0, 3 * sizeof(unsigned int)));
   RMD_CUDA_TRY(cudaMemset2D(s->conv, s->conv_pitch, 0, sizeof(int) * (size_t)w, h));
@@ -253,6 +259,8 @@ void seeds_free(rmd_seeds *s)
   delete s->copier;
   cudaFree(s->pc_points); cudaFree(s->pc_counts); cudaFree(s->pc_total);
   if(s->fan_ev) cudaEventDestroy(s->fan_ev);
+  if(s->ext_ev) cudaEventDestroy(s->ext_ev);
+  cudaFree(s->ref_u8);
   cudaFree(s->undist_xy); cudaFree(s->undist_frac); cudaFree(s->undist_tmp[0]); cudaFree(s->undist_tmp[1]);
   free(s->undist_host_xy); free(s->undist_host_frac);
   cudaGetLastError();
@@ -277,9 +285,25 @@ int ensure_matches(rmd_seeds *s)
   return 0;
 }
 
+// Orders s->stream after whatever another handle enqueued against this handle's buffers
+// (rmd_denoiser_run_seeds*: reads s->seed, writes the depth image rmd_seeds_point_cloud reads).
+int wait_external(rmd_seeds *s)
+{
+  if(s->ext_pending)
+  {
+    RMD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ext_ev, 0));
+    s->ext_pending = false;
+  }
+  return 0;
+}
+
 // Run the seed-initialisation kernel on the reference image now in s->ref.
 int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_depth, float max_depth)
 {
+  {
+    const int rc = wait_external(s);
+    if(rc) return rc;
+  }
   s->min_depth = min_depth;
   s->max_depth = max_depth;
   s->avg_depth = (min_depth + max_depth) / 2.0f;
@@ -319,6 +343,10 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   const float tx = T_curr_ref.m[3], ty = T_curr_ref.m[7], tz = T_curr_ref.m[11];
   s->dist_from_ref = sqrtf(tx * tx + ty * ty + tz * tz);                          // :125
 
+  {
+    const int rc = wait_external(s);
+    if(rc) return rc;
+  }
   s->frame_index += 1;
   FilterParams P;
   memset(&P, 0, sizeof(P));
@@ -415,6 +443,18 @@ cudaError_t u8_frame_to_float(rmd_seeds *s, const uint8_t *src, size_t src_pitch
                             s->stream);
 }
 
+// True when `p` lies in page-locked host memory the copy engine can read directly.
+bool is_page_locked(const void *p)
+{
+  cudaPointerAttributes attr;
+  if(cudaPointerGetAttributes(&attr, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
 // Stage a host frame (float or u8) into the next ring slot and make the
 // compute stream wait for it.  Returns the slot.
 int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *slot_out)
@@ -422,40 +462,48 @@ int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *
   const int slot = s->next_slot;
   s->next_slot = (slot + 1) % kSlots;
   const size_t row_bytes = elem_size * (size_t)s->width;
-  if(s->slot_used[slot])
+  // RMD_OPT_PINNED_INPUT: the caller's buffer is page-locked and stays untouched until the next sync,
+  // so the DMA reads it in place (no staging copy, no wait for the pinned ring slot)
+  const bool direct = s->pinned_input && is_page_locked(host_img);
+  const void *dma_src = host_img;
+  if(!direct)
   {
-    ProfScope prof(0);
-    RMD_CUDA_TRY(cudaEventSynchronize(s->copied[slot]));  // pinned buffer free again
-  }
-  if(!s->copier)
-  {
-    // helper threads for the ingest copy: RMD_COPY_THREADS, else an eighth of the
-    // machine (3..15).  One core stages a cold 1.2 MB frame in ~95 us, 4 in ~31 us,
-    // 16 in ~13 us (tools/copy_probe.cpp on the B200 host, 128 hardware threads).
-    const char *env = getenv("RMD_COPY_THREADS");
-    int helpers = env ? atoi(env) : (int)(std::thread::hardware_concurrency() / 8) - 1;
-    if(!env && helpers < 3) helpers = 3;
-    if(helpers < 0) helpers = 0;
-    if(helpers > 15) helpers = 15;
-    s->copier = new ParallelCopier(helpers);
-  }
-  {
-    ProfScope prof(1);
-    s->copier->copy(s->pinned[slot], host_img, row_bytes * s->height);
+    if(s->slot_used[slot])
+    {
+      ProfScope prof(0);
+      RMD_CUDA_TRY(cudaEventSynchronize(s->copied[slot]));  // pinned buffer free again
+    }
+    if(!s->copier)
+    {
+      // helper threads for the ingest copy: RMD_COPY_THREADS, else an eighth of the
+      // machine (3..15).  One core stages a cold 1.2 MB frame in ~95 us, 4 in ~31 us,
+      // 16 in ~13 us (tools/copy_probe.cpp on the B200 host, 128 hardware threads).
+      const char *env = getenv("RMD_COPY_THREADS");
+      int helpers = env ? atoi(env) : (int)(std::thread::hardware_concurrency() / 8) - 1;
+      if(!env && helpers < 3) helpers = 3;
+      if(helpers < 0) helpers = 0;
+      if(helpers > 15) helpers = 15;
+      s->copier = new ParallelCopier(helpers);
+    }
+    {
+      ProfScope prof(1);
+      s->copier->copy(s->pinned[slot], host_img, row_bytes * s->height);
+    }
+    dma_src = s->pinned[slot];
   }
   ProfScope prof_h2d(2);
   if(s->slot_used[slot])
     RMD_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->consumed[slot], 0));
   if(elem_size == sizeof(float))
   {
-    RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr[slot], s->curr_pitch, s->pinned[slot], row_bytes,
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr[slot], s->curr_pitch, dma_src, row_bytes,
                                    row_bytes, s->height, cudaMemcpyHostToDevice, s->copy_stream));
   }
   else
   {
     if(!s->curr_u8[slot])
       RMD_CUDA_TRY(cudaMallocPitch(&s->curr_u8[slot], &s->curr_u8_pitch, (size_t)s->width, s->height));
-    RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr_u8[slot], s->curr_u8_pitch, s->pinned[slot], row_bytes,
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr_u8[slot], s->curr_u8_pitch, dma_src, row_bytes,
                                    row_bytes, s->height, cudaMemcpyHostToDevice, s->copy_stream));
   }
   RMD_CUDA_TRY(cudaEventRecord(s->copied[slot], s->copy_stream));
@@ -583,6 +631,7 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   switch(option)
   {
   case RMD_OPT_RECORD_MATCHES: s->record_matches = (value != 0); return 0;
+  case RMD_OPT_PINNED_INPUT: s->pinned_input = (value != 0); return 0;
   case RMD_OPT_KERNEL_VARIANT:
     RMD_REQUIRE(value == 0 || value == 1, "RMD_OPT_KERNEL_VARIANT: 0 (staged) or 1 (direct)");
     s->variant = value;
@@ -647,12 +696,12 @@ int rmd_seeds_set_reference_u8(rmd_seeds_t *s, const uint8_t *host_img, const fl
 {
   RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_set_reference_u8: null argument");
   DeviceGuard guard(s->device);
-  if(!s->curr_u8[0])
-    RMD_CUDA_TRY(cudaMallocPitch(&s->curr_u8[0], &s->curr_u8_pitch, (size_t)s->width, s->height));
-  RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
-  RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr_u8[0], s->curr_u8_pitch, host_img, (size_t)s->width,
+  // own scratch image: the ring slots belong to frames that may still be in flight
+  if(!s->ref_u8)
+    RMD_CUDA_TRY(cudaMallocPitch(&s->ref_u8, &s->ref_u8_pitch, (size_t)s->width, s->height));
+  RMD_CUDA_TRY(cudaMemcpy2DAsync(s->ref_u8, s->ref_u8_pitch, host_img, (size_t)s->width,
                                  (size_t)s->width, s->height, cudaMemcpyHostToDevice, s->stream));
-  RMD_CUDA_TRY(u8_frame_to_float(s, s->curr_u8[0], s->curr_u8_pitch, s->ref, s->ref_pitch));
+  RMD_CUDA_TRY(u8_frame_to_float(s, s->ref_u8, s->ref_u8_pitch, s->ref, s->ref_pitch));
   s->n_total += 1;
   return finish_set_reference(s, T_curr_world, min_depth, max_depth);
 }
@@ -827,6 +876,10 @@ int point_cloud_run(rmd_seeds *s, const float *dev_depth, size_t depth_pitch_byt
 {
   if(!s->has_reference)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_point_cloud: set_reference has not been called");
+  {
+    const int rc = wait_external(s);
+    if(rc) return rc;
+  }
   const int n_pixels = s->width * s->height;
   PointCloudParams P;
   memset(&P, 0, sizeof(P));
@@ -984,6 +1037,10 @@ int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
 {
   RMD_REQUIRE(s && host_src, "rmd_seeds_upload_state: null argument");
   DeviceGuard guard(s->device);
+  {
+    const int rc = wait_external(s);
+    if(rc) return rc;
+  }
   const size_t w = s->width, h = s->height;
   if(is_seed_field(field))
   {
@@ -1313,8 +1370,8 @@ int rmd_denoiser_run(rmd_denoiser_t *d, const float *mu, size_t mu_pitch, const 
   DeviceGuard guard(d->device);
   // Inputs may have been produced on another stream (the seed matrix' own):
   // the reference runs everything on the legacy default stream, which orders
-  // it implicitly; here the caller's last call on the seeds handle
-  // (device_ptr) has already synchronised that stream.
+  // it implicitly; here they must be complete when this is called
+  // (rmd_seeds_device_ptr, which hands them out, synchronises that stream).
   DenoiseSetupParams P;
   memset(&P, 0, sizeof(P));
   denoiser_setup_common(d, P);
@@ -1344,6 +1401,10 @@ static int run_seeds_common(rmd_denoiser_t *d, rmd_seeds_t *s, float lambda, int
   P.seed = s->seed; P.seed_stride = s->seed_stride;
   RMD_CUDA_TRY(launch_denoise_setup(P, true, d->stream));
   d->n_total += 1;
+  // s->seed has been read once this kernel is done: later writers on s->stream (update,
+  // set_reference, upload_state) wait for it
+  RMD_CUDA_TRY(cudaEventRecord(s->ext_ev, d->stream));
+  s->ext_pending = true;
   return denoiser_iterate(d, lambda, iterations, buf);
 }
 
@@ -1370,7 +1431,13 @@ int rmd_denoiser_run_seeds_to_device(rmd_denoiser_t *d, rmd_seeds_t *s, float *d
   int buf = 0;
   const int rc = run_seeds_common(d, s, lambda, iterations, &buf);
   if(rc) return rc;
-  return denoiser_emit(d, buf, NULL, dev_out, out_pitch_bytes);
+  const int rc2 = denoiser_emit(d, buf, NULL, dev_out, out_pitch_bytes);
+  if(rc2) return rc2;
+  // dev_out is complete when this event fires: rmd_seeds_point_cloud(s, dev_out, ...) and everything
+  // else on the seeds' stream waits for it (the two streams are cudaStreamNonBlocking: no implicit order)
+  RMD_CUDA_TRY(cudaEventRecord(s->ext_ev, d->stream));
+  s->ext_pending = true;
+  return 0;
 }
 
 int rmd_denoiser_sync(rmd_denoiser_t *d)
@@ -1432,8 +1499,11 @@ extern "C"
 {
 
 // The reference's reducers run on the legacy default stream and block on a
-// 4-byte cudaMemcpy (src/reduction.cu:108,163); same here, so they order
-// after whatever the caller enqueued on blocking streams.
+// 4-byte cudaMemcpy (src/reduction.cu:108,163); same here.  The library's own
+// streams are cudaStreamNonBlocking, so the legacy stream does NOT order after
+// them: an image produced by a handle must be complete before it is reduced
+// (rmd_seeds_device_ptr synchronises; after rmd_seeds_copy_field_to_device call
+// rmd_seeds_sync first).
 int rmd_reduce_sum_f32(const float *dev_img, size_t stride, size_t width, size_t height, float *out)
 {
   RMD_REQUIRE(dev_img && out, "rmd_reduce_sum_f32: null argument");

@@ -110,10 +110,10 @@ private:
     unsigned long long seen = 0;
     for(;;)
     {
-      // spin for ~100 us, then sleep until the next job
-      // (2 ms: helpers stay hot at any frame rate above ~500 fps; a condition-variable
-      // wake-up costs more than the copy it would help with)
-      const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(2000);
+      // spin briefly, then sleep until the next job (0.5 ms: helpers stay hot at any
+      // frame rate above ~2000 fps -- below that a 13 us copy is not what limits the
+      // caller, and a node with several handles must not burn its cores spinning)
+      const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(500);
       unsigned long long now = generation_.load(std::memory_order_acquire);
       while(now == seen && std::chrono::steady_clock::now() < spin_until)
       {

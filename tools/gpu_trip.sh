@@ -1,0 +1,42 @@
+#!/bin/bash
+# One parameterised runner for everything that goes to the GPU box (replaces the
+# round-1 gpu_trip*.sh one-offs).  Usage, from the repo root:
+#   gpurun --timeout 1500 -- 'bash tools/gpu_trip.sh tests bench ncu_p5 ...'
+# Each word is a stage; outputs land in gpurun_out/.  Stages are independent and
+# each runs under its own `timeout`, so one hang cannot eat the lease.
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+OUT=gpurun_out
+BENCH_NCU="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+for stage in "$@"; do
+  echo "=== stage $stage $(date +%T)"
+  case "$stage" in
+    tests)      timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; tail -3 $OUT/pytest_gpu.log ;;
+    tests_all)  timeout 1800 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; tail -5 $OUT/pytest_gpu.log ;;
+    parity)     timeout 1500 python -m pytest tests/test_full_length_parity.py -m gpu -q -s > $OUT/pytest_parity.log 2>&1; tail -5 $OUT/pytest_parity.log ;;
+    smoke)      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log ;;
+    bench)      timeout 900 python bench.py > $OUT/bench_c2.json 2> $OUT/bench_c2.err; tail -c 600 $OUT/bench_c2.json ;;
+    bench_c3)   timeout 900 python bench.py --config c3 > $OUT/bench_c3.json 2> $OUT/bench_c3.err ;;
+    bench_c4)   timeout 900 python bench.py --config c4 > $OUT/bench_c4.json 2> $OUT/bench_c4.err ;;
+    bench_ref)  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_c2.json 2> $OUT/bench_ref_c2.err ;;
+    bench_ref_c3) timeout 900 python bench.py --impl reference --config c3 --steps 2 --warmup 1 > $OUT/bench_ref_c3.json 2> $OUT/bench_ref_c3.err ;;
+    bench_ref_c4) timeout 900 python bench.py --impl reference --config c4 --steps 1 --warmup 1 > $OUT/bench_ref_c4.json 2> $OUT/bench_ref_c4.err ;;
+    launches)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $OUT/launches_c2.csv $BENCH_NCU > $OUT/launches_c2.log 2>&1 ;;
+    launches_ref) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_ref_c2.csv python bench.py --impl reference --steps 1 --warmup 0 > $OUT/launches_ref_c2.log 2>&1 ;;
+    launches_c3) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_c3.csv $BENCH_NCU --config c3 > $OUT/launches_c3.log 2>&1 ;;
+    ncu_p5)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 3 -c 1 -f -o $OUT/prof_staged_p5_heavy $BENCH_NCU > $OUT/ncu_p5_heavy.log 2>&1
+                timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 129 -c 1 -f -o $OUT/prof_staged_p5_steady $BENCH_NCU > $OUT/ncu_p5_steady.log 2>&1 ;;
+    ncu_p7)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 3 -c 1 -f -o $OUT/prof_staged_p7_heavy $BENCH_NCU --config c4 --frames 140 > $OUT/ncu_p7_heavy.log 2>&1
+                timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 129 -c 1 -f -o $OUT/prof_staged_p7_steady $BENCH_NCU --config c4 --frames 140 > $OUT/ncu_p7_steady.log 2>&1 ;;
+    ncu_denoise) timeout 900 ncu --set full --clock-control none --import-source on -k regex:denoise_ -s 2 -c 2 -f -o $OUT/prof_denoise python tools/denoise_probe.py --once > $OUT/ncu_denoise.log 2>&1 ;;
+    denoise)    timeout 600 python tools/denoise_probe.py > $OUT/denoise_probe.txt 2>&1; tail -12 $OUT/denoise_probe.txt ;;
+    timeline)   timeout 600 python tools/timeline_probe.py > $OUT/timeline.txt 2>&1 ;;
+    tune)       timeout 900 python tools/tune_probe.py > $OUT/tune_probe.txt 2>&1; cat $OUT/tune_probe.txt ;;
+    multi_kf)   timeout 600 python tools/multi_keyframe_probe.py > $OUT/multi_keyframe_probe.txt 2>&1; cat $OUT/multi_keyframe_probe.txt ;;
+    extra)      timeout 900 python tests/perf/bench_extra.py > $OUT/bench_extra.json 2> $OUT/bench_extra.err ;;
+    e2e_probe)  timeout 600 python tools/e2e_probe.py > $OUT/e2e_probe.txt 2>&1 ;;
+    cpp)        timeout 900 python -m pytest tests/test_cpp_facade.py tests/test_cpp_multi_gpu.py -m gpu -q > $OUT/pytest_cpp.log 2>&1; tail -5 $OUT/pytest_cpp.log ;;
+    *)          echo "unknown stage $stage" ;;
+  esac
+done
+echo "=== done $(date +%T)"

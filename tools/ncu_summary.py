@@ -1,7 +1,8 @@
-"""Summarise two `ncu --set full` captures of the staged depth-filter kernel (a search-heavy and a
-steady-state frame) into profiles/r01_ncu_staged.{md,json}.  Runs where ncu is installed (no GPU needed):
+"""Summarise two `ncu --set full` captures of one kernel (A/B: e.g. a search-heavy and a steady-state frame of
+the staged depth-filter kernel) into profiles/<out>.{md,json}.  Runs where ncu is installed (no GPU needed):
 
-    python tools/ncu_summary.py gpurun_out/prof_staged_heavy.ncu-rep gpurun_out/prof_staged_steady.ncu-rep
+    python tools/ncu_summary.py gpurun_out/prof_staged_p5_heavy.ncu-rep gpurun_out/prof_staged_p5_steady.ncu-rep \
+        r02_ncu_staged "VGA, 5x5 patch" [algorithmic bytes per launch]
 """
 import csv
 import io
@@ -35,9 +36,12 @@ def raw(path):
 
 def main():
     heavy, steady = raw(sys.argv[1]), raw(sys.argv[2])
-    label = sys.argv[3] if len(sys.argv) > 3 else ""
-    out = {"traffic_bytes_per_launch": {}, "metrics": {}}
-    lines = ["| metric | heavy frame | steady frame |", "|---|---|---|"]
+    base = sys.argv[3] if len(sys.argv) > 3 else "r02_ncu_staged"
+    what = sys.argv[4] if len(sys.argv) > 4 else "VGA, 5x5 patch"
+    algo = float(sys.argv[5]) if len(sys.argv) > 5 else 15974400.0
+    names = (sys.argv[6], sys.argv[7]) if len(sys.argv) > 7 else ("heavy", "steady")
+    out = {"traffic_bytes_per_launch": {}, "metrics": {}, "what": what, "algorithmic_bytes_per_launch": algo}
+    lines = [f"| metric | {names[0]} | {names[1]} |", "|---|---|---|"]
     for m in METRICS:
         if m not in heavy:
             continue
@@ -50,20 +54,20 @@ def main():
             v, u = rep[m]
             tot += float(v.replace(",", "")) * TO_BYTES.get(u, 1.0)
         out["traffic_bytes_per_launch"][key] = tot
-    with open(os.path.join(ROOT, "profiles", "r01_ncu_staged.json"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", base + ".json"), "w") as f:
         json.dump(out, f, indent=1)
     t = out["traffic_bytes_per_launch"]
-    md = f"""# r01 -- ncu `--set full --clock-control none` captures of the fused depth-filter kernel (staged variant)
+    md = f"""# {base} -- ncu `--set full --clock-control none` captures: {what}
 
-Command: `ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s <n> -c 1 python bench.py --steps 1 --warmup 1 --no-cpu-baseline` on a B200 ({label}). VGA, 5x5 patch. *heavy* = 4th update after the keyframe (every interior seed searches), *steady* = 130th update (most seeds converged). Times under ncu are cold-cache/serialised; `bench.py` reports the CUDA-event times. Summary written by `tools/ncu_summary.py`.
+Captured with `tools/gpu_trip.sh` (stages ncu_*) on a B200; columns = {names[0]} / {names[1]} launch. Times under ncu are
+cold-cache and serialised; `bench.py` reports the CUDA-event times.  Written by `tools/ncu_summary.py`.
 
 """ + "\n".join(lines) + f"""
 
-DRAM traffic per launch (read + write): heavy {t['heavy'] / 1e6:.2f} MB, steady {t['steady'] / 1e6:.2f} MB; algorithmic bytes per launch 15.97 MB (52 B/px). Traffic is BELOW the algorithmic figure: absorbing seeds are skipped (4 B instead of 52 B), retired tiles are not visited at all, and the 13.5 MB seed state stays in the 126 MB L2 from frame to frame; the compulsory DRAM stream is the new 1.2 MB frame.
-
-Reading: the heavy frame is instruction-issue bound, not memory bound (issue slots ~3/4 busy, FMA and LSU pipes ~40 %, DRAM throughput below 1 %); per 32 candidates the kernel executes ~440 warp instructions of which 238 are the NCC arithmetic that bit-parity with the reference fixes (DESIGN.md 4.1). The steady frame is latency bound: ~10^7 warp instructions spread over ~800 tiles with a few work items each; its duration is the dependent chain of the busiest CTA (profiles/r01_staged_timeline.txt).
+DRAM traffic per launch (read + write): {names[0]} {t['heavy'] / 1e6:.2f} MB, {names[1]} {t['steady'] / 1e6:.2f} MB; algorithmic
+bytes per launch {algo / 1e6:.2f} MB.
 """
-    with open(os.path.join(ROOT, "profiles", "r01_ncu_staged.md"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", base + ".md"), "w") as f:
         f.write(md)
     print(md)
 
