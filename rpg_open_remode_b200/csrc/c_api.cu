@@ -166,6 +166,7 @@ struct rmd_seeds
   unsigned int *tile_arrivals;
   unsigned int *heavy_list[2], *light_list[2];  // work lists: this frame's / the next frame's
   unsigned int *work_counts;   // 3 rotating slots of {heavy, light, helpers, items}
+  unsigned int *cursor;        // {next work-list entry, CTAs out of work} of the persistent staged launch
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
@@ -213,9 +214,15 @@ int seeds_alloc(rmd_seeds *s)
   RMD_CUDA_TRY(cudaMemset2D(s->conv, s->conv_pitch, 0, sizeof(int) * (size_t)w, h));
   {
     s->n_tiles = ((w + staged::TILE_W - 1) / staged::TILE_W) * ((h + staged::TILE_H - 1) / staged::TILE_H);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    s->cta_slots = sms * 3;
+    // resident CTAs of the staged kernel = its persistent grid (SMs x occupancy: 3 per SM for 5x5, 2 for 7x7)
+    s->cta_slots = staged_cta_slots(s->patch);
+    if(s->cta_slots <= 0)
+    {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+      s->cta_slots = sms * (s->patch <= 5 ? 3 : 2);
+      cudaGetLastError();
+    }
     RMD_CUDA_TRY(cudaMalloc(&s->tile_keys, sizeof(unsigned long long) * (size_t)s->n_tiles * staged::NPIX));
     RMD_CUDA_TRY(cudaMalloc(&s->tile_arrivals, sizeof(unsigned int) * (size_t)s->n_tiles));
     s->tiles_x = (w + staged::TILE_W - 1) / staged::TILE_W;
@@ -225,6 +232,8 @@ int seeds_alloc(rmd_seeds *s)
       RMD_CUDA_TRY(cudaMalloc(&s->light_list[i], sizeof(unsigned int) * (size_t)s->n_tiles));
     }
     RMD_CUDA_TRY(cudaMalloc(&s->work_counts, 12 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMalloc(&s->cursor, 2 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMemset(s->cursor, 0, 2 * sizeof(unsigned int)));
   }
   RMD_CUDA_TRY(cudaEventCreate(&s->t0));
   RMD_CUDA_TRY(cudaEventCreate(&s->t1));
@@ -253,6 +262,7 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->tile_keys); cudaFree(s->tile_arrivals);
   cudaFree(s->heavy_list[0]); cudaFree(s->heavy_list[1]); cudaFree(s->light_list[0]); cudaFree(s->light_list[1]);
   cudaFree(s->work_counts);
+  cudaFree(s->cursor);
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
@@ -326,6 +336,7 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   // the first staged frame of a keyframe starts from the full work list; keys hold "no match"
   s->worklist_valid = false;
   RMD_CUDA_TRY(cudaMemsetAsync(s->tile_arrivals, 0, sizeof(unsigned int) * (size_t)s->n_tiles, s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->cursor, 0, 2 * sizeof(unsigned int), s->stream));
   RMD_CUDA_TRY(launch_fill_u64(s->tile_keys, (size_t)s->n_tiles * staged::NPIX, 0x407FFFFF00000000ull, s->stream));
   s->n_total += 1;
   s->n_total += 1;
@@ -336,8 +347,10 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   return 0;
 }
 
-// Enqueue the fused depth-filter kernel for the frame at (curr, pitch).
-int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const float *T_curr_world)
+// Host side of one update: pose chain, parameter block, TMA descriptors and -- when the keyframe's work
+// list is not valid (first frame, state upload, variant switch) -- its rebuild on the handle's stream.
+// Nothing is launched for the frame itself; `P` is ready for launch_depth_filter_*.
+int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const float *T_curr_world, FilterParams &P)
 {
   const Pose T_curr_ref = pose_compose(pose_from(T_curr_world), s->T_world_ref);  // seed_matrix.cu:124
   const float tx = T_curr_ref.m[3], ty = T_curr_ref.m[7], tz = T_curr_ref.m[11];
@@ -348,7 +361,6 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     if(rc) return rc;
   }
   s->frame_index += 1;
-  FilterParams P;
   memset(&P, 0, sizeof(P));
   P.width = s->width; P.height = s->height;
   P.seed = s->seed; P.seed_stride = s->seed_stride;
@@ -389,8 +401,6 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.counts_zero = s->work_counts + 4 * ((f + 1) % 3);
     P.retired_converged = s->counters + 2;
   }
-
-  if(s->timing) RMD_CUDA_TRY(cudaEventRecord(s->t0, s->stream));
   if(s->variant == 0)
   {
     if(!s->maps) s->maps = new StagedMaps();
@@ -399,7 +409,6 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
       const int rc = s->maps->encode(P, s->patch);
       if(rc) return rc;
     }
-    ProfScope prof_launch(4);
     if(!s->worklist_valid)
     {
       // every tile once, in image order, no helpers; nothing retired yet
@@ -411,23 +420,45 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     }
     if(s->timeline)
       RMD_CUDA_TRY(cudaMemsetAsync(s->timeline, 0, s->timeline_bytes, s->stream));
-    s->last_staged = true;
-    RMD_CUDA_TRY(launch_depth_filter_staged(P, *s->maps, s->patch, s->stream));
+  }
+  return 0;
+}
+
+// Book-keeping after the frame's kernel has been enqueued (by this handle or by a batched launch).
+void finish_update(rmd_seeds *s)
+{
+  s->last_staged = (s->variant == 0);
+  if(s->variant != 0)
+    s->worklist_valid = false;   // the direct kernel does not maintain the staged kernel's work list
+  s->n_fused += 1;
+  s->n_total += 1;
+  s->trust_conv = true;
+}
+
+// Enqueue the fused depth-filter kernel for the frame at (curr, pitch).
+int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const float *T_curr_world)
+{
+  FilterParams P;
+  const int rc = prepare_update(s, curr, curr_pitch, T_curr_world, P);
+  if(rc) return rc;
+  if(s->timing) RMD_CUDA_TRY(cudaEventRecord(s->t0, s->stream));
+  if(s->variant == 0)
+  {
+    ProfScope prof_launch(4);
+    const FilterParams *pp = &P;
+    const StagedMaps *mm = s->maps;
+    RMD_CUDA_TRY(launch_depth_filter_staged(&pp, &mm, 1, s->cursor, s->patch, s->stream));
   }
   else
   {
     RMD_CUDA_TRY(launch_depth_filter_direct(P, s->patch, s->stream));
-    s->worklist_valid = false;   // the direct kernel does not maintain the staged kernel's work list
-    s->last_staged = false;
   }
   if(s->timing)
   {
     RMD_CUDA_TRY(cudaEventRecord(s->t1, s->stream));
     s->t_valid = true;
   }
-  s->n_fused += 1;
-  s->n_total += 1;
-  s->trust_conv = true;
+  finish_update(s);
   return 0;
 }
 
@@ -767,19 +798,63 @@ int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t
   int slot = 0;
   const int rc = stage_host_frame(h0, host_img, elem_size, &slot);   // one pinned copy, one upload (+ ingest kernel)
   if(rc) return rc;
-  RMD_CUDA_TRY(cudaEventRecord(h0->fan_ev, h0->stream));            // the float frame is ready
-  for(int i = 1; i < n; ++i)
+  // ONE launch for all staged keyframes of h0's patch size (groups of STAGED_BATCH_MAX): their work lists
+  // are concatenated, so the dependent chains of different keyframes interleave on the GPU from the first
+  // cycle.  Keyframes on the direct variant (or of another patch size) are enqueued one by one.  Everything
+  // runs on h0's stream, where the frame lives.
+  RMD_REQUIRE(n <= 64, "rmd_seeds_update_many: at most 64 keyframes per call");
+  int batch_ids[64], single_ids[64], n_batch = 0, n_single = 0;
+  for(int i = 0; i < n; ++i)
   {
-    rmd_seeds *h = handles[i];
-    RMD_CUDA_TRY(cudaStreamWaitEvent(h->stream, h0->fan_ev, 0));
-    const int rci = enqueue_update(h, h0->curr[slot], h0->curr_pitch, T_curr_world);
-    if(rci) return rci;
-    RMD_CUDA_TRY(cudaEventRecord(h->fan_ev, h->stream));
+    const rmd_seeds *h = handles[i];
+    if(h0->variant == 0 && h->variant == 0 && h->patch == h0->patch) batch_ids[n_batch++] = i;
+    else single_ids[n_single++] = i;
   }
-  const int rc0 = enqueue_update(h0, h0->curr[slot], h0->curr_pitch, T_curr_world);
-  if(rc0) return rc0;
+  for(int g = 0; g < n_batch; g += STAGED_BATCH_MAX)
+  {
+    FilterParams P[STAGED_BATCH_MAX];
+    const FilterParams *pp[STAGED_BATCH_MAX];
+    const StagedMaps *mm[STAGED_BATCH_MAX];
+    const int m = (n_batch - g < STAGED_BATCH_MAX) ? n_batch - g : STAGED_BATCH_MAX;
+    for(int k = 0; k < m; ++k)
+    {
+      rmd_seeds *h = handles[batch_ids[g + k]];
+      const int rci = prepare_update(h, h0->curr[slot], h0->curr_pitch, T_curr_world, P[k]);
+      if(rci) return rci;
+      if(h != h0)
+      {
+        // whatever is pending on the keyframe's own stream (set_reference, work-list rebuild) comes first
+        RMD_CUDA_TRY(cudaEventRecord(h->fan_ev, h->stream));
+        RMD_CUDA_TRY(cudaStreamWaitEvent(h0->stream, h->fan_ev, 0));
+      }
+      pp[k] = &P[k];
+      mm[k] = h->maps;
+    }
+    {
+      ProfScope prof_launch(4);
+      RMD_CUDA_TRY(launch_depth_filter_staged(pp, mm, m, h0->cursor, h0->patch, h0->stream));
+    }
+    for(int k = 0; k < m; ++k)
+      finish_update(handles[batch_ids[g + k]]);
+  }
+  for(int j = 0; j < n_single; ++j)
+  {
+    rmd_seeds *h = handles[single_ids[j]];
+    if(h != h0)
+    {
+      RMD_CUDA_TRY(cudaEventRecord(h->fan_ev, h->stream));
+      RMD_CUDA_TRY(cudaStreamWaitEvent(h0->stream, h->fan_ev, 0));
+    }
+    const cudaStream_t own = h->stream;
+    h->stream = h0->stream;
+    const int rci = enqueue_update(h, h0->curr[slot], h0->curr_pitch, T_curr_world);
+    h->stream = own;
+    if(rci) return rci;
+  }
+  // everything ran on h0's stream: the other keyframes' own streams continue after it
+  RMD_CUDA_TRY(cudaEventRecord(h0->fan_ev, h0->stream));
   for(int i = 1; i < n; ++i)
-    RMD_CUDA_TRY(cudaStreamWaitEvent(h0->stream, handles[i]->fan_ev, 0));   // the slot is free when ALL have read it
+    RMD_CUDA_TRY(cudaStreamWaitEvent(handles[i]->stream, h0->fan_ev, 0));
   RMD_CUDA_TRY(cudaEventRecord(h0->consumed[slot], h0->stream));
   return 0;
 }
@@ -1197,15 +1272,14 @@ struct rmd_denoiser
   int device;
   int width, height, stride;
   cudaStream_t own_stream, stream;
-  float4 *state[2];
-  float2 *gmu;
-  float *dense_out;
+  // planar solver state (denoiser.cu): one allocation of 10 planes of stride x height floats --
+  // (u, u_head, p.x, p.y) twice (ping-pong between launches), then g and the noisy depth
+  float *planes;
+  float *state[2][4];
+  float *g, *noisy;
+  CUtensorMap map_state[2][4], map_g, map_noisy;   // TMA descriptors of the planes (fixed for the handle's life)
   float large_sigma_sq;
   uint64_t n_total;
-  // the iteration loop as a CUDA graph (launch-bound: ~3 us kernels), cached per (iterations, lambda)
-  cudaGraphExec_t loop_exec;
-  int loop_iterations;
-  float loop_lambda;
 };
 
 namespace
@@ -1213,55 +1287,28 @@ namespace
 
 int denoiser_iterate(rmd_denoiser *d, float lambda, int iterations, int *final_buf)
 {
-  DenoiseStepParams sp;
-  sp.width = d->width; sp.height = d->height; sp.stride = d->stride;
-  sp.gmu = d->gmu;
+  DenoiseBlockParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.width = d->width; bp.height = d->height; bp.stride = d->stride;
+  bp.g = d->map_g; bp.mu = d->map_noisy;
   const float L = sqrtf(8.0f);          // depthmap_denoiser.cu:130
-  sp.tau = 0.02f;                       // :131
-  sp.sigma = (1 / (L * L)) / sp.tau;    // :132
-  sp.theta = 0.5f;                      // :133
-  sp.lambda = lambda;
+  bp.tau = 0.02f;                       // :131
+  bp.sigma = (1 / (L * L)) / bp.tau;    // :132
+  bp.theta = 0.5f;                      // :133
+  bp.lambda = lambda;
   int cur = 0;
-  const bool use_graph = iterations >= 8;
-  if(use_graph && !(d->loop_exec && d->loop_iterations == iterations && d->loop_lambda == lambda))
+  // DENOISE_T iterations per launch (temporal blocking); the last launch takes the remainder
+  for(int left = iterations; left > 0; left -= DENOISE_T)
   {
-    if(d->loop_exec) { cudaGraphExecDestroy(d->loop_exec); d->loop_exec = NULL; }
-    cudaGraph_t graph = NULL;
-    RMD_CUDA_TRY(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
-    cudaError_t err = cudaSuccess;
-    int c = 0;
-    for(int i = 0; i < iterations && err == cudaSuccess; ++i)
-    {
-      sp.in = d->state[c];
-      sp.out = d->state[c ^ 1];
-      err = launch_denoise_step(sp, d->stream);
-      c ^= 1;
-    }
-    const cudaError_t end_err = cudaStreamEndCapture(d->stream, &graph);
-    if(err != cudaSuccess) { if(graph) cudaGraphDestroy(graph); return fail_cuda(err, "denoise: capture"); }
-    RMD_CUDA_TRY(end_err);
-    err = cudaGraphInstantiate(&d->loop_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if(err != cudaSuccess) { d->loop_exec = NULL; return fail_cuda(err, "cudaGraphInstantiate"); }
-    d->loop_iterations = iterations;
-    d->loop_lambda = lambda;
+    bp.n_it = left < DENOISE_T ? left : DENOISE_T;
+    bp.in_u = d->map_state[cur][0]; bp.in_uh = d->map_state[cur][1];
+    bp.in_px = d->map_state[cur][2]; bp.in_py = d->map_state[cur][3];
+    bp.out_u = d->state[cur ^ 1][0]; bp.out_uh = d->state[cur ^ 1][1];
+    bp.out_px = d->state[cur ^ 1][2]; bp.out_py = d->state[cur ^ 1][3];
+    RMD_CUDA_TRY(launch_denoise_block(bp, d->stream));
+    d->n_total += 1;
+    cur ^= 1;
   }
-  if(use_graph)
-  {
-    RMD_CUDA_TRY(cudaGraphLaunch(d->loop_exec, d->stream));
-    cur = iterations & 1;
-  }
-  else
-  {
-    for(int i = 0; i < iterations; ++i)
-    {
-      sp.in = d->state[cur];
-      sp.out = d->state[cur ^ 1];
-      RMD_CUDA_TRY(launch_denoise_step(sp, d->stream));
-      cur ^= 1;
-    }
-  }
-  d->n_total += (uint64_t)(iterations > 0 ? iterations : 0);
   *final_buf = cur;
   return 0;
 }
@@ -1270,26 +1317,22 @@ int denoiser_setup_common(rmd_denoiser *d, DenoiseSetupParams &P)
 {
   P.width = d->width; P.height = d->height;
   P.large_sigma_sq = d->large_sigma_sq;
-  P.gmu = d->gmu; P.state = d->state[0]; P.stride = d->stride;
+  P.g = d->g; P.noisy = d->noisy;
+  P.u = d->state[0][0]; P.u_head = d->state[0][1]; P.p_x = d->state[0][2]; P.p_y = d->state[0][3];
+  P.stride = d->stride;
   return 0;
 }
 
 int denoiser_emit(rmd_denoiser *d, int buf, float *host_out, float *dev_out, size_t dev_pitch)
 {
-  const size_t w = d->width, h = d->height;
+  const size_t row = sizeof(float) * (size_t)d->width, pitch = sizeof(float) * (size_t)d->stride;
+  const float *u = d->state[buf][0];   // the denoised depth is the primal variable itself: no export kernel
   if(dev_out)
   {
-    RMD_CUDA_TRY(launch_export_plane(reinterpret_cast<const float*>(d->state[buf]), d->stride * 4, 4, 0,
-                                     dev_out, (int)(dev_pitch / sizeof(float)), d->width, d->height,
-                                     d->stream));
-    d->n_total += 1;
+    RMD_CUDA_TRY(cudaMemcpy2DAsync(dev_out, dev_pitch, u, pitch, row, d->height, cudaMemcpyDeviceToDevice, d->stream));
     return 0;
   }
-  RMD_CUDA_TRY(launch_export_plane(reinterpret_cast<const float*>(d->state[buf]), d->stride * 4, 4, 0,
-                                   d->dense_out, d->width, d->width, d->height, d->stream));
-  d->n_total += 1;
-  RMD_CUDA_TRY(cudaMemcpyAsync(host_out, d->dense_out, sizeof(float) * w * h, cudaMemcpyDeviceToHost,
-                               d->stream));
+  RMD_CUDA_TRY(cudaMemcpy2DAsync(host_out, row, u, pitch, row, d->height, cudaMemcpyDeviceToHost, d->stream));
   RMD_CUDA_TRY(cudaStreamSynchronize(d->stream));  // u_.getDevData is blocking, :223
   return 0;
 }
@@ -1315,14 +1358,28 @@ int rmd_denoiser_create(int width, int height, int device, rmd_denoiser_t **out)
   d->large_sigma_sq = -1.0f;  // "not set" (the reference leaves it uninitialised)
   cudaError_t err = cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking);
   const size_t n = (size_t)d->stride * height;
-  if(err == cudaSuccess) err = cudaMalloc(&d->state[0], sizeof(float4) * n);
-  if(err == cudaSuccess) err = cudaMalloc(&d->state[1], sizeof(float4) * n);
-  if(err == cudaSuccess) err = cudaMalloc(&d->gmu, sizeof(float2) * n);
-  if(err == cudaSuccess) err = cudaMalloc(&d->dense_out, sizeof(float) * (size_t)width * height);
+  if(err == cudaSuccess) err = cudaMalloc(&d->planes, sizeof(float) * n * 10);
   if(err != cudaSuccess)
   {
     rmd_denoiser_destroy(d);
     return fail_cuda(err, "rmd_denoiser_create");
+  }
+  for(int b = 0; b < 2; ++b)
+    for(int k = 0; k < 4; ++k)
+      d->state[b][k] = d->planes + n * (size_t)(4 * b + k);
+  d->g = d->planes + n * 8;
+  d->noisy = d->planes + n * 9;
+  int rc = 0;
+  for(int b = 0; b < 2 && !rc; ++b)
+    for(int k = 0; k < 4 && !rc; ++k)
+      rc = encode_tensor_map_2d_f32(&d->map_state[b][k], d->state[b][k], width, height, d->stride,
+                                    DENOISE_EXT_W, DENOISE_EXT_H);
+  if(!rc) rc = encode_tensor_map_2d_f32(&d->map_g, d->g, width, height, d->stride, DENOISE_EXT_W, DENOISE_EXT_H);
+  if(!rc) rc = encode_tensor_map_2d_f32(&d->map_noisy, d->noisy, width, height, d->stride, DENOISE_EXT_W, DENOISE_EXT_H);
+  if(rc)
+  {
+    rmd_denoiser_destroy(d);
+    return rc;
   }
   d->stream = d->own_stream;
   *out = d;
@@ -1335,8 +1392,7 @@ int rmd_denoiser_destroy(rmd_denoiser_t *d)
   DeviceGuard guard(d->device);
   cudaDeviceSynchronize();
   if(d->own_stream) cudaStreamDestroy(d->own_stream);
-  if(d->loop_exec) cudaGraphExecDestroy(d->loop_exec);
-  cudaFree(d->state[0]); cudaFree(d->state[1]); cudaFree(d->gmu); cudaFree(d->dense_out);
+  cudaFree(d->planes);
   cudaGetLastError();
   delete d;
   return 0;

@@ -28,8 +28,13 @@ cudaError_t launch_depth_filter_direct(const FilterParams &P, int patch_side, cu
 // TMA-staged shared-memory variant (depth_filter_staged.cu).  `maps` is the
 // host-side descriptor set built by StagedMaps::encode for this frame.
 struct StagedMaps;
-cudaError_t launch_depth_filter_staged(const FilterParams &P, const StagedMaps &maps,
-                                       int patch_side, cudaStream_t stream);
+// One launch for n keyframes (n = 1: the single-keyframe instantiation).  Persistent grid: one CTA per
+// resident slot, each pulling entries of the keyframes' work lists through `cursor` (2 zero-initialised
+// uints owned by the caller; the kernel leaves them at zero).
+cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const StagedMaps *const *maps, int n,
+                                       unsigned int *cursor, int patch_side, cudaStream_t stream);
+// Resident CTAs of the staged kernel on the current device (SMs x occupancy), 0 on error.
+int staged_cta_slots(int patch_side);
 
 // dst[i] = value for i < n (64-bit pattern fill)
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);

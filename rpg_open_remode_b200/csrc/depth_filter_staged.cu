@@ -35,9 +35,13 @@
 
 #include <limits.h>
 
+#include <algorithm>
+#include <mutex>
+
 #include "depth_filter.cuh"
 #include "depth_filter_math.cuh"
 #include "staged_maps.cuh"
+#include "denoiser.cuh"
 
 // 1: the debug timeline also counts the candidates scored from the strip and
 // from global memory (slots 8, 9).  Off by default: even predicated off, the
@@ -78,6 +82,7 @@ struct __align__(128) StagedSmem
   int centroid[3];   // sum of x * w, y * w, w over the seeds (w = accepted candidates, x/y = middle of their range)
   int strip_ox, strip_oy, strip_w, strip_rows;
   int is_last;
+  unsigned int fetch;                  // index of the work-list entry this CTA processes next (persistent loop)
   int items_acc;                       // work items of the tile (sum of the seeds' chunk counts)
   unsigned int row_active[TILE_H];     // ballot of the seeds to update, per pixel row
   unsigned long long mbar;
@@ -157,58 +162,22 @@ __device__ __forceinline__ int to_int_clamped(float v)
 
 } // namespace
 
+// One entry of a keyframe's work list: phases 0-4 for one tile (or one share of a split tile).
+// `mbar_phase` is the parity of the CTA's TMA mbarrier, carried from tile to tile.
 template<int PS>
-__global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_staged_kernel(
-    const __grid_constant__ FilterParams P, const __grid_constant__ StagedTensorMaps M)
+__device__ __forceinline__ void process_tile(const FilterParams &P, const StagedTensorMaps &M, StagedSmem<PS> &S,
+                                             const unsigned int entry, unsigned int &mbar_phase)
 {
-  extern __shared__ unsigned char smem_raw[];
-  // 128-byte alignment for the TMA destinations, derived as an offset from
-  // smem_raw so that the compiler keeps the shared address space (LDS/STS).
-  const unsigned int smem_pad = (128u - (smem_addr(smem_raw) & 127u)) & 127u;
-  StagedSmem<PS> &S = *reinterpret_cast<StagedSmem<PS>*>(smem_raw + smem_pad);
-
-  // Launched with programmatic stream serialisation: this grid may be set up
-  // while the previous frame's kernel drains; nothing may be read before that
-  // kernel has completed and flushed (a no-op for an ordinary launch).
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // pdl == 2: let the next frame's CTAs take the slots this frame's tail leaves
-  // idle (they park at their own griddepcontrol.wait until this grid is done)
-  if(P.pdl == 2)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x, wid = threadIdx.y;   // warp `wid` owns pixel row `wid` of the tile
   const int tid = wid * TILE_W + lane;
   const int pix = tid;
-  if(blockIdx.x == 0 && tid == 0)
-  {
-    *P.converged_next = 0u;
-    P.counts_zero[0] = 0u; P.counts_zero[1] = 0u; P.counts_zero[2] = 0u; P.counts_zero[3] = 0u;
-  }
-  // ---- which tile, and which share of it.  The lead CTAs of the PREVIOUS frame
-  // wrote this frame's work list: tiles that were busy come first (a frame ends
-  // when its slowest CTA does, so those must start at once), and a tile that
-  // was much busier than the per-slot average is listed zeff times -- its lead
-  // CTA and zeff - 1 helpers, each taking every zeff-th round of its work
-  // list (once most seeds have converged a frame's duration is bounded below by
-  // its busiest tile, up to 9216 items).  Light tiles follow; tiles with
-  // nothing left to update, ever, are not listed; surplus CTAs exit.
-  int tile, z, zeff;
-  {
-    const unsigned int b = blockIdx.x;
-    // (the heavy list has one slot per launched CTA: load the entry together with
-    // the counts -- one memory round trip instead of two for the busy tiles)
-    const unsigned int e_heavy = P.heavy_cur[b];
-    const unsigned int n_heavy = P.counts_cur[0], n_light = P.counts_cur[1];
-    unsigned int e;
-    if(b < n_heavy)
-      e = e_heavy;
-    else if(b - n_heavy < n_light)
-      e = P.light_cur[b - n_heavy];
-    else
-      return;
-    tile = (int)(e & 0xfffffu);
-    z = (int)((e >> 20) & 0x3fu);
-    zeff = (int)(e >> 26);
-  }
+  // entry = tile | share << 20 | zeff << 26.  A tile that was much busier than the per-slot average of the
+  // previous frame is listed zeff times -- its lead CTA and zeff - 1 helpers, each taking every zeff-th round
+  // of its work list (once most seeds have converged a frame's duration is bounded below by its busiest
+  // tile, up to 9216 items).
+  const int tile = (int)(entry & 0xfffffu);
+  const int z = (int)((entry >> 20) & 0x3fu);
+  const int zeff = (int)(entry >> 26);
   const int x0 = (tile % P.tiles_x) * TILE_W, y0 = (tile / P.tiles_x) * TILE_H;
   const int x = x0 + lane, y = y0 + wid;
   const bool lead = (z == 0);  // the CTA that records what all of them compute identically
@@ -272,7 +241,6 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     S.n_levels = 0;
     for(int i = 0; i < 8; ++i) S.dbg[i] = 0;
     S.centroid[0] = 0; S.centroid[1] = 0; S.centroid[2] = 0;
-    mbar_init(&S.mbar, 1);
   }
   const unsigned int conv_ballot = __ballot_sync(0xffffffffu, converged);
   const int n_active = __syncthreads_count(active);
@@ -673,7 +641,8 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   }
   __syncthreads();  // publishes the work list and the strip geometry (built while the TMA is in flight)
   const int strip_ox = S.strip_ox, strip_oy = S.strip_oy, strip_w = S.strip_w, strip_rows = S.strip_rows;
-  mbar_wait(&S.mbar, 0);
+  mbar_wait(&S.mbar, mbar_phase);
+  mbar_phase ^= 1u;
   RMD_STAMP(3);
   // The warps of the tile's zeff CTAs take 32-item rounds of the list round-robin.
   const int total = S.level_cum[n_levels];
@@ -848,6 +817,90 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   }
   RMD_STAMP(5);
 }
+#undef RMD_STAMP
+
+// The launch: a persistent grid (one CTA per resident slot).  Every CTA pulls entries of the frame's work
+// list(s) through one cursor until they run out, so a frame costs one wave however many tiles it lists:
+// no empty CTAs (the list's capacity is tiles + 1024 entries, of which a steady frame uses a third), no wave
+// transition, and the busy tiles -- listed first -- are still started first.  The lead CTAs of the PREVIOUS
+// frame wrote this frame's lists: tiles that were busy come first (a frame ends when its slowest CTA does),
+// a tile that was much busier than the per-slot average is listed zeff times (3b), light tiles follow; tiles
+// with nothing left to update, ever, are not listed.  K > 1: the lists of up to K keyframes (independent
+// reference views updated by the same incoming frame) are concatenated -- all heavy lists, then all light
+// lists -- so the dependent chains of different keyframes interleave from the first cycle.
+template<int PS, int K>
+__global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_staged_kernel(
+    const __grid_constant__ StagedBatch<K> B)
+{
+  extern __shared__ unsigned char smem_raw[];
+  // 128-byte alignment for the TMA destinations, derived as an offset from
+  // smem_raw so that the compiler keeps the shared address space (LDS/STS).
+  const unsigned int smem_pad = (128u - (smem_addr(smem_raw) & 127u)) & 127u;
+  StagedSmem<PS> &S = *reinterpret_cast<StagedSmem<PS>*>(smem_raw + smem_pad);
+
+  // Launched with programmatic stream serialisation: this grid may be set up
+  // while the previous frame's kernel drains; nothing may be read before that
+  // kernel has completed and flushed (a no-op for an ordinary launch).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int n_kf = (K == 1) ? 1 : B.n;
+  const int tid = threadIdx.y * TILE_W + threadIdx.x;
+  if(blockIdx.x == 0 && tid == 0)
+  {
+    for(int k = 0; k < n_kf; ++k)
+    {
+      const FilterParams &P = B.p[K == 1 ? 0 : k];
+      *P.converged_next = 0u;
+      P.counts_zero[0] = 0u; P.counts_zero[1] = 0u; P.counts_zero[2] = 0u; P.counts_zero[3] = 0u;
+    }
+  }
+  if(tid == 0)
+    mbar_init(&S.mbar, 1);
+  unsigned int mbar_phase = 0u;
+  for(;;)
+  {
+    if(tid == 0)
+      S.fetch = atomicAdd(B.cursor, 1u);
+    __syncthreads();   // also: everybody is done with the previous tile's shared memory (and sees the mbarrier)
+    const unsigned int i = S.fetch;
+    // entry i of the concatenation: heavy lists of keyframes 0..n-1, then their light lists
+    int kf = -1;
+    unsigned int entry = 0u;
+    {
+      unsigned int base = 0u;
+#pragma unroll 1
+      for(int k = 0; k < n_kf && kf < 0; ++k)
+      {
+        const FilterParams &P = B.p[K == 1 ? 0 : k];
+        const unsigned int n_heavy = P.counts_cur[0];
+        if(i - base < n_heavy) { kf = k; entry = P.heavy_cur[i - base]; }
+        base += n_heavy;
+      }
+#pragma unroll 1
+      for(int k = 0; k < n_kf && kf < 0; ++k)
+      {
+        const FilterParams &P = B.p[K == 1 ? 0 : k];
+        const unsigned int n_light = P.counts_cur[1];
+        if(i - base < n_light) { kf = k; entry = P.light_cur[i - base]; }
+        base += n_light;
+      }
+    }
+    if(kf < 0)
+      break;           // the lists are exhausted (uniform: every thread read the same index)
+    process_tile<PS>(B.p[K == 1 ? 0 : kf], B.m[K == 1 ? 0 : kf], S, entry, mbar_phase);
+    __syncthreads();   // S.fetch and the tile's shared state are free again
+  }
+  // the last CTA out rewinds the cursor for the next launch (launches on a stream are ordered)
+  if(tid == 0)
+  {
+    __threadfence();
+    const unsigned int done = atomicAdd(B.cursor + 1, 1u);
+    if(done == gridDim.x - 1u)
+    {
+      B.cursor[0] = 0u;
+      B.cursor[1] = 0u;
+    }
+  }
+}
 
 // ---------------------------------------------------------------- host side
 
@@ -899,6 +952,12 @@ int encode_one(CUtensorMap *map, const void *base, int width, int height, int st
 
 } // namespace
 
+int encode_tensor_map_2d_f32(CUtensorMap *map, const void *base, int width, int height, int stride_floats,
+                             int box_w, int box_h)
+{
+  return encode_one(map, base, width, height, stride_floats, box_w, box_h);
+}
+
 int StagedMaps::encode(const FilterParams &P, int patch_side)
 {
   if(((uintptr_t)P.ref % 16) != 0 || ((uintptr_t)P.curr % 16) != 0 || (P.ref_stride % 4) != 0 ||
@@ -926,37 +985,97 @@ int StagedMaps::encode(const FilterParams &P, int patch_side)
   return 0;
 }
 
-template<int PS>
-static cudaError_t launch_staged(const FilterParams &P, const StagedMaps &maps, cudaStream_t stream)
+namespace
 {
-  static bool configured[64] = {false};
-  const size_t smem = sizeof(StagedSmem<PS>) + 128;  // slack for the manual 128-byte alignment
-  int device = 0;
-  cudaGetDevice(&device);
-  if(device < 0 || device >= 64 || !configured[device])
+
+template<int PS, int K>
+struct StagedLaunch
+{
+  static size_t smem_bytes() { return sizeof(StagedSmem<PS>) + 128; }  // slack for the manual 128-byte alignment
+
+  // Resident CTAs on `device` (SMs x occupancy); configures the kernel's shared-memory limit on first use.
+  static int slots(int device)
   {
-    const cudaError_t err = cudaFuncSetAttribute(depth_filter_staged_kernel<PS>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if(err != cudaSuccess) return err;
-    if(device >= 0 && device < 64) configured[device] = true;
+    static std::mutex mutex;
+    static int cached[64] = {0};
+    std::lock_guard<std::mutex> lock(mutex);
+    if(device < 0 || device >= 64)
+      return 0;
+    if(cached[device] == 0)
+    {
+      if(cudaFuncSetAttribute(depth_filter_staged_kernel<PS, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)smem_bytes()) != cudaSuccess)
+        return 0;
+      int per_sm = 0, sms = 0;
+      if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_filter_staged_kernel<PS, K>, NTHREADS,
+                                                       smem_bytes()) != cudaSuccess ||
+         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+        return 0;
+      cached[device] = per_sm * sms;
+    }
+    return cached[device];
   }
-  const dim3 block(TILE_W, NWARPS);
-  const dim3 grid(P.n_tiles + P.helper_cap);  // capacity of the work list; surplus CTAs exit at once
-  cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = P.pdl ? 1 : 0;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, depth_filter_staged_kernel<PS>, P, maps.maps);
+
+  static cudaError_t launch(const FilterParams *const *P, const StagedMaps *const *maps, int n,
+                            unsigned int *cursor, cudaStream_t stream)
+  {
+    int device = 0;
+    cudaError_t err = cudaGetDevice(&device);
+    if(err != cudaSuccess) return err;
+    const int n_slots = slots(device);
+    if(n_slots <= 0)
+    {
+      err = cudaGetLastError();
+      return err != cudaSuccess ? err : cudaErrorInvalidDevice;
+    }
+    static_assert(sizeof(StagedBatch<K>) <= 32000, "kernel parameter space (32 KB from CUDA 12.1)");
+    StagedBatch<K> B;
+    memset(&B, 0, sizeof(B));
+    int tiles = 0;
+    for(int k = 0; k < n; ++k)
+    {
+      B.p[k] = *P[k];
+      B.m[k] = maps[k]->maps;
+      tiles += P[k]->n_tiles + P[k]->helper_cap;
+    }
+    B.cursor = cursor;
+    B.n = n;
+    const dim3 block(TILE_W, NWARPS);
+    const dim3 grid(std::min(n_slots, tiles));   // persistent: never more CTAs than can be resident
+    cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem_bytes(); cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = P[0]->pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, depth_filter_staged_kernel<PS, K>, B);
+  }
+};
+
+} // namespace
+
+cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const StagedMaps *const *maps, int n,
+                                       unsigned int *cursor, int patch_side, cudaStream_t stream)
+{
+  if(n < 1 || n > STAGED_BATCH_MAX || !P || !maps || !cursor)
+    return cudaErrorInvalidValue;
+  if(patch_side == 5)
+    return n == 1 ? StagedLaunch<5, 1>::launch(P, maps, n, cursor, stream)
+                  : StagedLaunch<5, STAGED_BATCH_MAX>::launch(P, maps, n, cursor, stream);
+  if(patch_side == 7)
+    return n == 1 ? StagedLaunch<7, 1>::launch(P, maps, n, cursor, stream)
+                  : StagedLaunch<7, STAGED_BATCH_MAX>::launch(P, maps, n, cursor, stream);
+  return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_depth_filter_staged(const FilterParams &P, const StagedMaps &maps, int patch_side,
-                                       cudaStream_t stream)
+int staged_cta_slots(int patch_side)
 {
-  if(patch_side == 5) return launch_staged<5>(P, maps, stream);
-  if(patch_side == 7) return launch_staged<7>(P, maps, stream);
-  return cudaErrorInvalidValue;
+  int device = 0;
+  if(cudaGetDevice(&device) != cudaSuccess)
+    return 0;
+  if(patch_side == 5) return StagedLaunch<5, 1>::slots(device);
+  if(patch_side == 7) return StagedLaunch<7, 1>::slots(device);
+  return 0;
 }
 
 } // namespace rmdb

@@ -48,6 +48,26 @@ struct alignas(64) StagedTensorMaps
   CUtensorMap curr[staged::NUM_WIDTHS];    // boxes strip_width(i) x STRIP_BOX_ROWS
 };
 
+// Most keyframes one launch can serve (rmd_seeds_update_many: several live reference views against
+// one incoming frame).
+constexpr int STAGED_BATCH_MAX = 8;
+
+// Everything one launch of the staged kernel receives, as ONE __grid_constant__ parameter: the
+// descriptors and parameter blocks of 1 (single-keyframe instantiation: all offsets static) or up
+// to STAGED_BATCH_MAX keyframes (batched instantiation: indexed by the keyframe an entry belongs
+// to), and the launch's work cursor.  8 keyframes = 8 x (640 + sizeof(FilterParams)) bytes: needs
+// the 32 KB kernel-parameter space of CUDA >= 12.1.
+template<int K>
+struct alignas(64) StagedBatch
+{
+  StagedTensorMaps m[K];
+  FilterParams p[K];
+  // cursor[0]: next entry of the concatenated work lists (all heavy lists, then all light lists);
+  // cursor[1]: CTAs that have run out of work.  The last CTA out leaves both at zero.
+  unsigned int *cursor;
+  int n;                 // keyframes in this launch, 1 <= n <= K
+};
+
 // Tiled 2-D tensor maps (cuTensorMapEncodeTiled) over the pitched reference
 // and current images.  Box shapes are fixed when a map is encoded; the box
 // origin is a run-time coordinate of the TMA instruction, so one map per box

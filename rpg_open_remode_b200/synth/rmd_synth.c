@@ -193,10 +193,14 @@ int rmd_synth_render(const void *p, const float *T_world_cam, uint8_t *img_u8,
       const float dy = T[4] * xc + T[5] * yc + T[6];
       const float dz = T[8] * xc + T[9] * yc + T[10];
       float t_hit;
-      if (dz >= -1e-6f || oz <= s->h_max) {
-        t_hit = 10.0f; /* never happens on the generated trajectories */
+      if (dz >= -1e-6f) {
+        t_hit = 10.0f; /* a ray that does not descend: never happens on the generated trajectories */
       } else {
-        const float t_top = (s->h_max - oz) / dz;
+        /* h_max (the SUM of all bump heights + box) only bounds the height field; a camera below
+         * that bound is still above the terrain, so its rays start at the camera itself.  (Round 1
+         * sent every ray of such a camera to t = 10: keyframe seeds 1, 3, 4, 5 and the 1080p seed
+         * rendered a view-dependent shell instead of the scene, and nothing could converge.) */
+        const float t_top = oz > s->h_max ? (s->h_max - oz) / dz : 0.0f;
         const float t_bot = (0.0f - oz) / dz;
         const float dt = (t_bot - t_top) / (float)n_march;
         float t_lo = t_top, t_hi = t_bot;

@@ -42,3 +42,20 @@ def test_product_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode != 0, "bench.py must not produce a number without the CUDA path"
     assert not any(l.strip().startswith("{") for l in res.stdout.splitlines()), res.stdout
+
+
+def test_every_package_attribute_the_gpu_scripts_use_exists():
+    """bench.py and the GPU-box tools only run where a B200 is: a misspelt or un-exported name must not cost a lease."""
+    import re
+    import rpg_open_remode_b200 as rmd
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for d in ("tools", os.path.join("tests", "perf")):
+        files += [os.path.join(ROOT, d, f) for f in sorted(os.listdir(os.path.join(ROOT, d))) if f.endswith(".py")]
+    missing = []
+    for path in files:
+        with open(path) as f:
+            src = f.read()
+        for name in set(re.findall(r"\brmd\.([A-Za-z_][A-Za-z_0-9]*)", src)):
+            if not hasattr(rmd, name):
+                missing.append((os.path.relpath(path, ROOT), name))
+    assert not missing, missing

@@ -32,6 +32,7 @@ import pytest
 
 import oracle_binding as ob
 import rpg_open_remode_b200 as rmd
+from rpg_open_remode_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -283,7 +284,29 @@ def test_denoiser_parity(qvga_sequence, iters):
     got_planar = den.denoise(g.getMu(), g.getSigmaSq(), g.getA(), g.getB(), 0.5, iters)
     assert np.array_equal(got_seeds, got_planar)
     assert np.abs(got_seeds - want).max() <= 1e-4 * rng_d
-    assert den.launchCount() >= 2 * iters
+    # temporal blocking: 8 iterations per launch (csrc/denoiser.cu), plus the set-up kernel, two calls
+    assert den.launchCount() == 2 * (1 + (iters + 7) // 8)
+
+
+@pytest.mark.parametrize("size", [(101, 77), (33, 17), (320, 240), (49, 25)])
+def test_denoiser_ragged_sizes_and_iteration_counts(size):
+    """Tile seams (48 x 24 tiles + 8-pixel halo), partial tiles, odd widths (pixel pairs), images smaller than one
+    tile, and iteration counts around the 8-iterations-per-launch block: all against the Jacobi oracle."""
+    W, H = size
+    seq = synth.SyntheticSequence(W, H, seed=0x5EED0020 + W)
+    g, o = _pair(seq, matches=False)
+    _, rng_d = _set_reference(seq, g, o)
+    for k in range(1, 10):
+        f = seq.frame(k, want_depth=False)
+        g.update(f.image, f.T_cam_world)
+    mu, s2, a, b = g.downloadDepthmap(), g.downloadSigmaSq(), g.downloadA(), g.downloadB()
+    den = rmd.DepthmapDenoiser(W, H)
+    den.setLargeSigmaSq(rng_d)
+    for iters in (0, 1, 7, 8, 9, 16, 17, 40):
+        want = ob.denoise(mu, s2, a, b, rng_d, 0.5, iters)
+        got = den.denoiseSeeds(g, 0.5, iters)
+        assert np.abs(got - want).max() <= 1e-4 * rng_d, (size, iters, float(np.abs(got - want).max() / rng_d))
+    assert np.array_equal(den.denoiseSeeds(g, 0.5, 0), mu)
 
 
 def test_denoiser_requires_large_sigma(small_sequence):

@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
-STAGED5 = "_ZN4rmdb26depth_filter_staged_kernelILi5EEEvNS_12FilterParamsENS_16StagedTensorMapsE"
+STAGED5 = "_ZN4rmdb26depth_filter_staged_kernelILi5ELi1EEEvNS_11StagedBatchIXT0_EEE"
 
 pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump not installed")
 

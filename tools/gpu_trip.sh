@@ -34,6 +34,7 @@ for stage in "$@"; do
     tune)       timeout 900 python tools/tune_probe.py > $OUT/tune_probe.txt 2>&1; cat $OUT/tune_probe.txt ;;
     multi_kf)   timeout 600 python tools/multi_keyframe_probe.py > $OUT/multi_keyframe_probe.txt 2>&1; cat $OUT/multi_keyframe_probe.txt ;;
     extra)      timeout 900 python tests/perf/bench_extra.py > $OUT/bench_extra.json 2> $OUT/bench_extra.err ;;
+    parity_diag) timeout 900 python tools/parity_diag.py > $OUT/parity_diag.txt 2>&1; tail -n 30 $OUT/parity_diag.txt ;;
     e2e_probe)  timeout 600 python tools/e2e_probe.py > $OUT/e2e_probe.txt 2>&1 ;;
     cpp)        timeout 900 python -m pytest tests/test_cpp_facade.py tests/test_cpp_multi_gpu.py -m gpu -q > $OUT/pytest_cpp.log 2>&1; tail -5 $OUT/pytest_cpp.log ;;
     *)          echo "unknown stage $stage" ;;
