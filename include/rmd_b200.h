@@ -113,6 +113,7 @@ enum rmd_seeds_option {
 
 typedef struct rmd_seeds rmd_seeds_t;
 typedef struct rmd_denoiser rmd_denoiser_t;
+typedef struct rmd_multi rmd_multi_t;
 
 /* ------------------------------------------------------------------ misc */
 int rmd_abi_version(void);
@@ -308,6 +309,42 @@ int rmd_reduce_count_eq_i32(const int32_t *dev_img, size_t stride,
 /* extras the north star asks for (not in the reference) */
 int rmd_reduce_min_max_f32(const float *dev_img, size_t stride, size_t width,
                            size_t height, float *out_min, float *out_max);
+
+/* -------------------------------------------------------------- multi-GPU */
+
+/* Independent reference keyframes, one rmd_seeds_t per GPU.  The
+ * depth filter never reads a neighbour's or another keyframe's state
+ * (src/seed_check.cu, src/epipolar_match.cu, src/seed_update.cu), so there is
+ * no data-path collective: the only exchange is the FINAL GATHER of every
+ * keyframe's depth (f32) and convergence (i32) map to one root GPU -- grouped
+ * ncclSend / ncclRecv over NVLink.  The reference has no multi-GPU path (one
+ * SeedMatrix on the current device, src/check_cuda_device.cu:109).  NCCL
+ * (libnccl.so.2) is loaded at run time; without it these functions return
+ * RMD_ERR_UNSUPPORTED.
+ *
+ * One process driving n GPUs (e.g. a node owning several rmd::Depthmap
+ * objects): rank i <-> devices[i]; ncclCommInitAll. */
+int rmd_multi_create(const int *devices, int n, int width, int height, rmd_multi_t **out);
+/* One process per GPU: rank 0 calls rmd_multi_unique_id, ships the 128 bytes to
+ * the other ranks by its own means, every rank calls rmd_multi_create_rank
+ * (collective: ncclCommInitRank).  device < 0: current. */
+int rmd_multi_unique_id(char id[128]);
+int rmd_multi_create_rank(const char id[128], int n_ranks, int rank, int device, int width,
+                          int height, rmd_multi_t **out);
+int rmd_multi_destroy(rmd_multi_t *m);
+int rmd_multi_size(rmd_multi_t *m, int *n_ranks, int *n_local, int *first_rank);
+/* The final gather.  seeds[i]: keyframe of local member i (n entries after
+ * rmd_multi_create, one after rmd_multi_create_rank), whose queued updates are
+ * waited for on the device.  dev_depth (may be NULL, entries may be NULL): a
+ * pitched device image to send instead of the seeds' own depth estimate, e.g.
+ * the denoised map of rmd_denoiser_run_seeds_to_device (complete when this is
+ * called: rmd_denoiser_sync).  On the process that holds rank `root`,
+ * host_depth / host_conv receive n_ranks * width * height elements each, rank
+ * after rank; elsewhere they may be NULL.  Collective over all ranks; returns
+ * when the exchange has finished. */
+int rmd_multi_gather_maps(rmd_multi_t *m, rmd_seeds_t *const *seeds,
+                          const float *const *dev_depth, const size_t *dev_depth_pitch,
+                          int root, float *host_depth, int32_t *host_conv);
 
 /* ---------------------------------------------------------- device image */
 

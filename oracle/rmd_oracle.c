@@ -341,8 +341,13 @@ void rmd_oracle_stage_match(rmd_oracle_seeds *s, const float *curr,
 
       const f2 epi_line = {px_max.x - px_min.x, px_max.y - px_min.y};
       const f2 epi_dir = normalize2(epi_line); /* :74 */
-      const float half_length =
+      float half_length =
           0.5f * fmin_host(norm2(epi_line), (float)MAX_EXTENT_EPIPOLAR_SEARCH);
+      /* Defined deviation 2: a NaN / infinite segment (sigma_sq < 0: the variance of a
+       * collapsed seed is a rounding residue of either sign) makes the reference walk 143 candidates at NaN
+       * texture coordinates -- hardware-defined; measured on B200 it reports NO_MATCH.  Here, as in the
+       * product: no candidates, NO_MATCH. */
+      if (!isfinite(dot2(epi_line, epi_line))) half_length = NAN;
 
       const float sum_templ = s->sum_templ[k];
       const float const_templ_denom = s->const_templ_denom[k];

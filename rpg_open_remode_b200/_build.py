@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "librmd_b200.so")
 
-CUDA_SOURCES = ["c_api.cu", "depth_filter.cu", "depth_filter_staged.cu", "denoiser.cu", "reduction.cu", "ingest.cu", "point_cloud.cu"]
+CUDA_SOURCES = ["c_api.cu", "depth_filter.cu", "depth_filter_staged.cu", "denoiser.cu", "reduction.cu", "ingest.cu", "point_cloud.cu",
+                "multi_gpu.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",
@@ -60,7 +61,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + log[-1])
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread",
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread", "-ldl",
                                                       ]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)

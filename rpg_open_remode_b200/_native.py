@@ -63,6 +63,12 @@ _SIGNATURES = {
     "rmd_denoiser_run_seeds_to_device": (ci, [vp, vp, vp, cs, cf, ci]),
     "rmd_denoiser_sync": (ci, [vp]),
     "rmd_denoiser_launch_count": (ci, [vp, P(u64)]),
+    "rmd_multi_create": (ci, [P(ci), ci, ci, ci, P(vp)]),
+    "rmd_multi_unique_id": (ci, [ctypes.c_char_p]),
+    "rmd_multi_create_rank": (ci, [ctypes.c_char_p, ci, ci, ci, ci, ci, P(vp)]),
+    "rmd_multi_destroy": (ci, [vp]),
+    "rmd_multi_size": (ci, [vp, P(ci), P(ci), P(ci)]),
+    "rmd_multi_gather_maps": (ci, [vp, P(vp), P(vp), P(cs), ci, vp, vp]),
     "rmd_reduce_sum_f32": (ci, [vp, cs, cs, cs, P(cf)]),
     "rmd_reduce_sum_i32": (ci, [vp, cs, cs, cs, P(ctypes.c_int32)]),
     "rmd_reduce_count_eq_i32": (ci, [vp, cs, cs, cs, ctypes.c_int32, P(cs)]),

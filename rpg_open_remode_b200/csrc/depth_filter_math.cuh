@@ -89,12 +89,21 @@ __device__ __forceinline__ EpiSegment epipolar_segment(
   const float len_sq = line.x * line.x + line.y * line.y;
   const float inv_len = rsqrtf(len_sq);
   s.dir = make_float2(line.x * inv_len, line.y * inv_len);
-  // A zero-length segment (exact identity motion) makes the reference divide
-  // 0 by 0 and sample its texture at NaN coordinates (SURVEY.md 8a note 4).
-  // Defined behaviour here: one candidate at the mean projection.
-  if(!(len_sq > 0.0f))
+  // Two defined deviations, both where the reference samples its texture at NaN coordinates
+  // (hardware-defined results):
+  // 1. an exactly zero-length segment (exact identity motion) makes the reference divide 0 by 0 (SURVEY.md 8a
+  //    note 4); here: one candidate at the mean projection;
+  // 2. a NaN or infinite segment -- in practice sigma_sq < 0: the posterior variance
+  //    c1 (s^2 + m^2) + c2 (sigma^2 + mu^2) - mu'^2 (seed_update.cu:105) of a seed whose variance has collapsed
+  //    is a rounding residue of either sign, and sqrtf of a negative one is NaN.  fminf drops the NaN, so the
+  //    reference walks 143 candidates at NaN coordinates; measured on B200 (tools/parity_diag.py) it reports
+  //    NO_MATCH for such seeds frame after frame (b += 1, mu and sigma_sq frozen).  Here: no candidates, hence
+  //    NO_MATCH -- the same fate, without the 143 wasted patches.
+  if(len_sq == 0.0f)
     s.dir = make_float2(0.0f, 0.0f);
   s.half_len = 0.5f * fminf(sqrtf(len_sq), RMD_MAX_EPIPOLAR_EXTENT);
+  if(!(fabsf(len_sq) < CUDART_INF_F))
+    s.half_len = CUDART_NAN_F;     // `l <= half_len` is never true: the search loop does not run
   return s;
 }
 

@@ -34,6 +34,7 @@
 #include <cudaTypedefs.h>
 
 #include <limits.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <mutex>
@@ -1059,11 +1060,14 @@ cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const Stage
 {
   if(n < 1 || n > STAGED_BATCH_MAX || !P || !maps || !cursor)
     return cudaErrorInvalidValue;
+  // RMD_FORCE_BATCH_KERNEL=1 (test hook): single keyframes also go through the batched instantiation
+  static const bool force_batch = (getenv("RMD_FORCE_BATCH_KERNEL") != NULL);
+  const bool single = (n == 1) && !force_batch;
   if(patch_side == 5)
-    return n == 1 ? StagedLaunch<5, 1>::launch(P, maps, n, cursor, stream)
+    return single ? StagedLaunch<5, 1>::launch(P, maps, n, cursor, stream)
                   : StagedLaunch<5, STAGED_BATCH_MAX>::launch(P, maps, n, cursor, stream);
   if(patch_side == 7)
-    return n == 1 ? StagedLaunch<7, 1>::launch(P, maps, n, cursor, stream)
+    return single ? StagedLaunch<7, 1>::launch(P, maps, n, cursor, stream)
                   : StagedLaunch<7, STAGED_BATCH_MAX>::launch(P, maps, n, cursor, stream);
   return cudaErrorInvalidValue;
 }

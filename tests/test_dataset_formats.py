@@ -4,6 +4,8 @@ field mapping (src/depthmap_node.cpp:97-132, test/publish_dataset.cpp:77-100) an
 import os
 
 import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import pytest
 
 from rpg_open_remode_b200 import dataset as ds
@@ -124,3 +126,48 @@ def test_dataset_main_protocol_call_order(tiny_dataset):
     assert calls[0][3] == pytest.approx(depths[0].min() / 100, rel=1e-6)      # min/max of the frame's own depth map (:75-76)
     assert np.array_equal(calls[2][2], ds.Dataset.readCameraPose(d(2)).inv().data)   # T_curr_world = T_world_curr.inv() (:88,:101)
     assert res["depthmap"][0, 0] == 6 and res["denoised"][0, 0] == 7 and res["mean_update_s"] >= 0 and res["var_update_s"] >= 0
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_dataset_experiment_end_to_end_on_gpu(tmp_path):
+    """test/dataset_main.cpp end to end on the GPU (tools/dataset_main.py's path): a sequence written in the data
+    set's on-disk formats (sequence file, PNG, .depth text in cm) is read back by rmd::test::Dataset's mirror and
+    driven through rmd::Depthmap (8-bit frames, poses parsed from quaternions) -- the result equals feeding the same
+    parsed frames to a SeedMatrix by hand, converges, and reproduces the ray-cast ground truth."""
+    import importlib.util
+    import rpg_open_remode_b200 as rmd
+    from rpg_open_remode_b200 import dataset as ds
+    spec = importlib.util.spec_from_file_location("dataset_main", os.path.join(ROOT, "tools", "dataset_main.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    W, H, N = 320, 240, 60
+    cam = tool.write_synthetic(str(tmp_path), n=N, w=W, h=H, seed=0x5EED0002)
+    d = ds.Dataset("first_200_frames_traj_over_table_input_sequence.txt", str(tmp_path))
+    assert d.readDataSequence(0, 200) and len(d) == N
+    depthmap = rmd.Depthmap(W, H, cam[0], cam[2], cam[1], cam[3])
+    res = ds.run_dataset_experiment(depthmap, d, W, H, log=lambda *a: None)
+    assert res["updates"] == N - 1 and res["depthmap"].shape == (H, W)
+    # by hand, through the SeedMatrix-level API, with the same parsed inputs
+    seeds = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*cam))
+    gt = None
+    for k, e in enumerate(d):
+        img = d.readImage(e)
+        T = ds.Dataset.readCameraPose(e).inv()
+        if k == 0:
+            gt = d.readDepthmap(e, W, H)
+            seeds.setReferenceImage(img, T, float(gt.min()), float(gt.max()))
+        else:
+            seeds.update(img, T)
+    assert np.array_equal(res["depthmap"], seeds.downloadDepthmap())
+    depthmap.downloadConvergenceMap()
+    conv = depthmap.getConvergenceMap()
+    assert np.array_equal(conv, seeds.downloadConvergence())
+    c = conv == 1
+    rng_d = float(gt.max() - gt.min())
+    assert c.mean() > 0.5 and depthmap.getConvergedPercentage() == pytest.approx(100.0 * c.mean(), abs=1e-3)
+    assert np.median(np.abs(res["depthmap"] - gt)[c]) < 0.01 * rng_d
+    # the denoised map (0.5, 200 as test/dataset_main.cpp:116) stays inside the raw map's range and close to it
+    den = res["denoised"]
+    assert den.min() >= res["depthmap"].min() - 1e-5 and den.max() <= res["depthmap"].max() + 1e-5
+    assert np.median(np.abs(den - gt)[c]) < 0.01 * rng_d

@@ -16,11 +16,11 @@ import rpg_open_remode_b200 as rmd  # noqa: E402
 from rpg_open_remode_b200 import dataset as ds  # noqa: E402
 
 
-def write_synthetic(path, n=200, w=640, h=480):
+def write_synthetic(path, n=200, w=640, h=480, seed=0x5EED0001):
     """A synthetic sequence in the data set's on-disk layout (sequence file, images/*.png, depthmaps/*.depth)."""
     import cv2
     from rpg_open_remode_b200 import synth
-    seq = synth.SyntheticSequence(w, h, seed=0x5EED0001)
+    seq = synth.SyntheticSequence(w, h, seed=seed)
     os.makedirs(os.path.join(path, "images"))
     os.makedirs(os.path.join(path, "depthmaps"))
     lines = []

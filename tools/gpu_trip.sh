@@ -35,6 +35,12 @@ for stage in "$@"; do
     multi_kf)   timeout 600 python tools/multi_keyframe_probe.py > $OUT/multi_keyframe_probe.txt 2>&1; cat $OUT/multi_keyframe_probe.txt ;;
     extra)      timeout 900 python tests/perf/bench_extra.py > $OUT/bench_extra.json 2> $OUT/bench_extra.err ;;
     parity_diag) timeout 900 python tools/parity_diag.py > $OUT/parity_diag.txt 2>&1; tail -n 30 $OUT/parity_diag.txt ;;
+    batch_debug) timeout 300 python tools/batch_debug.py same 2 > $OUT/batch_debug.txt 2>&1
+                timeout 300 python tools/batch_debug.py diff 3 >> $OUT/batch_debug.txt 2>&1
+                RMD_FORCE_BATCH_KERNEL=1 timeout 600 python -m pytest tests/test_gpu_worklist.py -m gpu -q -x >> $OUT/batch_debug.txt 2>&1
+                tail -n 40 $OUT/batch_debug.txt ;;
+    sanitize)   timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/batch_debug.py diff 3 > $OUT/sanitize_memcheck.txt 2>&1; tail -n 15 $OUT/sanitize_memcheck.txt
+                timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/batch_debug.py same 2 > $OUT/sanitize_racecheck.txt 2>&1; tail -n 15 $OUT/sanitize_racecheck.txt ;;
     e2e_probe)  timeout 600 python tools/e2e_probe.py > $OUT/e2e_probe.txt 2>&1 ;;
     cpp)        timeout 900 python -m pytest tests/test_cpp_facade.py tests/test_cpp_multi_gpu.py -m gpu -q > $OUT/pytest_cpp.log 2>&1; tail -5 $OUT/pytest_cpp.log ;;
     *)          echo "unknown stage $stage" ;;
