@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) depth_filter_direct_kernel(const __grid_c
         float2 best_px = make_float2(0.0f, 0.0f);
         for(float l = -seg.half_len; l <= seg.half_len; l += RMD_EPIPOLAR_STEP)
         {
-          const float2 px = make_float2(seg.mean.x + l * seg.dir.x, seg.mean.y + l * seg.dir.y);
+          const float2 px = candidate_px(seg.mean.x, seg.mean.y, seg.dir.x, seg.dir.y, l);
           if(candidate_rejected<PS>(px, P.width, P.height))
             continue;
           const TapFrame frame = tap_frame<PS>(px, P.tex_quant);

@@ -57,6 +57,46 @@ __device__ __forceinline__ float2 project(const Camera &cam, const float3 p)
   return make_float2(cam.fx * p.x / p.z + cam.cx, cam.fy * p.y / p.z + cam.cy);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Every rounding of the per-seed and per-candidate arithmetic is PINNED.
+//
+// The reference builds with -use_fast_math, i.e. nvcc contracts a*b + c*d into ONE fused multiply-add
+// and one plain product -- and which of the two products stays plain is ptxas' choice (it depends on
+// which operand is ready first, so it differs between otherwise identical instantiations of the same
+// source: measured here, a kernel that reads the pose from a dynamically indexed parameter block
+// rounded ~12 % of the updated seeds differently, by 1-2 ulp, from the one that reads it from fixed
+// constant-bank slots).  Results that are bit-identical to the reference's own build
+// (tests/test_ref_cuda_parity.py) must not hang on such a choice: below, every sum of products is
+// written with explicit __fmaf_rn / __fmul_rn in exactly the form the reference's kernels
+// (src/epipolar_match.cu:60-123, src/seed_update.cu:40-121, src/triangulation.cu:30-68, rebuilt for
+// sm_100a: oracle/_ref) and the round-1 build of this file compile to -- read off their SASS -- so
+// that every kernel that includes this header (direct, staged, batched; 5x5 and 7x7) performs the same
+// roundings whatever ptxas would have chosen.  The pattern throughout: in x*a + y*b (+ z*c) the y
+// product is the plain one, x and z are fused onto it.
+// Divisions are the fast-math form x * rcp.approx(y), as -use_fast_math emits them.
+
+__device__ __forceinline__ float rcp_approx(const float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// a.x*b.x + a.y*b.y + a.z*b.z as the reference's build rounds it: the y product is the plain one
+__device__ __forceinline__ float dot3_pinned(const float3 a, const float3 b)
+{
+  return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+}
+
+// normalize(cam.cam2world(px)) inside the update: pinhole_camera.cuh:40-46, helper_math.h:1309-1313
+__device__ __forceinline__ float3 unit_bearing_pinned(const Camera &cam, const float u, const float v)
+{
+  const float px = __fmul_rn(__fadd_rn(u, -cam.cx), rcp_approx(cam.fx));
+  const float py = __fmul_rn(__fadd_rn(v, -cam.cy), rcp_approx(cam.fy));
+  const float inv = rsqrtf(__fadd_rn(__fmaf_rn(px, px, __fmul_rn(py, py)), 1.0f));
+  return make_float3(__fmul_rn(px, inv), __fmul_rn(py, inv), inv);
+}
+
 // src/seed_check.cu:53-66 (border handled by the caller)
 __device__ __forceinline__ int classify_seed(const FilterParams &P, const float4 seed)
 {
@@ -76,19 +116,35 @@ struct EpiSegment
   float half_len;   // half of min(segment length, 100 px)
 };
 
+// se3.cuh:164-168 + pinhole_camera.cuh:48-53: project(cam, T * p), roundings pinned
+__device__ __forceinline__ float2 transform_project_pinned(const Camera &cam, const Pose &T, const float3 p)
+{
+  const float X = __fadd_rn(__fmaf_rn(p.z, T.m[2], __fmaf_rn(p.x, T.m[0], __fmul_rn(p.y, T.m[1]))), T.m[3]);
+  const float Y = __fadd_rn(__fmaf_rn(p.z, T.m[6], __fmaf_rn(p.x, T.m[4], __fmul_rn(p.y, T.m[5]))), T.m[7]);
+  const float Z = __fadd_rn(__fmaf_rn(p.z, T.m[10], __fmaf_rn(p.x, T.m[8], __fmul_rn(p.y, T.m[9]))), T.m[11]);
+  const float inv_z = rcp_approx(Z);
+  return make_float2(__fmaf_rn(__fmul_rn(X, cam.fx), inv_z, cam.cx), __fmaf_rn(__fmul_rn(Y, cam.fy), inv_z, cam.cy));
+}
+
+__device__ __forceinline__ float3 scaled_pinned(const float3 v, const float s)
+{
+  return make_float3(__fmul_rn(v.x, s), __fmul_rn(v.y, s), __fmul_rn(v.z, s));
+}
+
 __device__ __forceinline__ EpiSegment epipolar_segment(
     const FilterParams &P, const int x, const int y, const float mu, const float sigma_sq)
 {
   const float sigma = sqrtf(sigma_sq);
-  const float3 f = unit_bearing(P.cam, (float)x, (float)y);
+  const float3 f = unit_bearing_pinned(P.cam, (float)x, (float)y);
   EpiSegment s;
-  s.mean = project(P.cam, transform(P.T_curr_ref, scaled(f, mu)));
-  const float2 lo = project(P.cam, transform(P.T_curr_ref, scaled(f, fmaxf(mu - 3.0f * sigma, 0.01f))));
-  const float2 hi = project(P.cam, transform(P.T_curr_ref, scaled(f, mu + (3.0f * sigma))));
-  const float2 line = make_float2(hi.x - lo.x, hi.y - lo.y);
-  const float len_sq = line.x * line.x + line.y * line.y;
+  s.mean = transform_project_pinned(P.cam, P.T_curr_ref, scaled_pinned(f, mu));
+  const float2 lo = transform_project_pinned(P.cam, P.T_curr_ref,
+                                             scaled_pinned(f, fmaxf(__fmaf_rn(sigma, -3.0f, mu), 0.01f)));
+  const float2 hi = transform_project_pinned(P.cam, P.T_curr_ref, scaled_pinned(f, __fmaf_rn(sigma, 3.0f, mu)));
+  const float2 line = make_float2(__fadd_rn(hi.x, -lo.x), __fadd_rn(hi.y, -lo.y));
+  const float len_sq = __fmaf_rn(line.x, line.x, __fmul_rn(line.y, line.y));
   const float inv_len = rsqrtf(len_sq);
-  s.dir = make_float2(line.x * inv_len, line.y * inv_len);
+  s.dir = make_float2(__fmul_rn(line.x, inv_len), __fmul_rn(line.y, inv_len));
   // Two defined deviations, both where the reference samples its texture at NaN coordinates
   // (hardware-defined results):
   // 1. an exactly zero-length segment (exact identity motion) makes the reference divide 0 by 0 (SURVEY.md 8a
@@ -101,7 +157,7 @@ __device__ __forceinline__ EpiSegment epipolar_segment(
   //    NO_MATCH -- the same fate, without the 143 wasted patches.
   if(len_sq == 0.0f)
     s.dir = make_float2(0.0f, 0.0f);
-  s.half_len = 0.5f * fminf(sqrtf(len_sq), RMD_MAX_EPIPOLAR_EXTENT);
+  s.half_len = __fmul_rn(fminf(sqrtf(len_sq), RMD_MAX_EPIPOLAR_EXTENT), 0.5f);
   if(!(fabsf(len_sq) < CUDART_INF_F))
     s.half_len = CUDART_NAN_F;     // `l <= half_len` is never true: the search loop does not run
   return s;
@@ -114,6 +170,13 @@ __device__ __forceinline__ bool candidate_rejected(const float2 px, const int wi
 {
   return (px.x >= (float)(width - PS)) || (px.y >= (float)(height - PS)) ||
          (px.x < (float)PS) || (px.y < (float)PS);
+}
+
+// Candidate l of a segment: px_mean + l * epi_dir (src/epipolar_match.cu:90), one fused multiply-add per axis.
+__device__ __forceinline__ float2 candidate_px(const float mean_x, const float mean_y, const float dir_x,
+                                               const float dir_y, const float l)
+{
+  return make_float2(__fmaf_rn(l, dir_x, mean_x), __fmaf_rn(l, dir_y, mean_y));
 }
 
 // Integer origin and (optionally quantised) bilinear weights of a candidate.
@@ -130,32 +193,32 @@ struct TapFrame
 template<int PS>
 __device__ __forceinline__ TapFrame tap_frame(const float2 px, const float quant)
 {
-  const float bx = px.x + (float)(-(PS / 2));
-  const float by = px.y + (float)(-(PS / 2));
+  const float bx = __fadd_rn(px.x, (float)(-(PS / 2)));
+  const float by = __fadd_rn(px.y, (float)(-(PS / 2)));
   TapFrame t;
   float al, be;
   if(quant > 0.0f)
   {
-    const float inv_q = 1.0f / quant;
-    const float tx = floorf(bx * quant + 0.5f);
-    const float ty = floorf(by * quant + 0.5f);
-    const float fi = floorf(tx * inv_q);
-    const float fj = floorf(ty * inv_q);
+    const float inv_q = rcp_approx(quant);
+    const float tx = floorf(__fmaf_rn(bx, quant, 0.5f));
+    const float ty = floorf(__fmaf_rn(by, quant, 0.5f));
+    const float fi = floorf(__fmul_rn(tx, inv_q));
+    const float fj = floorf(__fmul_rn(ty, inv_q));
     t.i0 = (int)fi;
     t.j0 = (int)fj;
-    al = (tx - fi * quant) * inv_q;
-    be = (ty - fj * quant) * inv_q;
+    al = __fmul_rn(__fmaf_rn(-fi, quant, tx), inv_q);
+    be = __fmul_rn(__fmaf_rn(-fj, quant, ty), inv_q);
   }
   else
   {
     const float fi = floorf(bx), fj = floorf(by);
     t.i0 = (int)fi;
     t.j0 = (int)fj;
-    al = bx - fi;
-    be = by - fj;
+    al = __fadd_rn(bx, -fi);
+    be = __fadd_rn(by, -fj);
   }
-  t.wx1 = al; t.wx0 = 1.0f - al;
-  t.wy1 = be; t.wy0 = 1.0f - be;
+  t.wx1 = al; t.wx0 = __fadd_rn(1.0f, -al);
+  t.wy1 = be; t.wy0 = __fadd_rn(1.0f, -be);
   return t;
 }
 
@@ -201,26 +264,26 @@ __device__ __forceinline__ float ncc_score(
     }
     float lower[PS];
 #pragma unroll
-    for(int i = 0; i < PS; ++i) lower[i] = t.wx0 * v[i] + t.wx1 * v[i + 1];
+    for(int i = 0; i < PS; ++i) lower[i] = __fmaf_rn(v[i], t.wx0, __fmul_rn(v[i + 1], t.wx1));
     if(j > 0)
     {
 #pragma unroll
       for(int i = 0; i < PS; ++i)
       {
-        const float img = t.wy0 * upper[i] + t.wy1 * lower[i];
+        const float img = __fmaf_rn(upper[i], t.wy0, __fmul_rn(lower[i], t.wy1));
         const float tv = templ[(j - 1) * PS + i];
-        sum_img += img;
-        sum_img_sq += img * img;
-        sum_img_templ += img * tv;
+        sum_img = __fadd_rn(sum_img, img);
+        sum_img_sq = __fmaf_rn(img, img, sum_img_sq);
+        sum_img_templ = __fmaf_rn(img, tv, sum_img_templ);
       }
     }
 #pragma unroll
     for(int i = 0; i < PS; ++i) upper[i] = lower[i];
   }
   const float area = (float)(PS * PS);
-  const float numerator = area * sum_img_templ - sum_img * sum_templ;
-  const float denominator = (area * sum_img_sq - sum_img * sum_img) * const_templ_denom;
-  return numerator * rsqrtf(denominator + FLT_MIN);
+  const float numerator = __fmaf_rn(sum_img_templ, area, -__fmul_rn(sum_img, sum_templ));
+  const float spread = __fmaf_rn(sum_img_sq, area, -__fmul_rn(sum_img, sum_img));
+  return __fmul_rn(numerator, rsqrtf(__fmaf_rn(const_templ_denom, spread, FLT_MIN)));
 }
 
 // Texel block of a candidate read straight from a pitched global image
@@ -239,83 +302,89 @@ struct GlobalTaps
   }
 };
 
-// src/triangulation.cu:30-50
-__device__ __forceinline__ float3 triangulate_midpoint(
-    const float3 f_ref, const float3 f_curr, const Pose &T_ref_curr)
-{
-  const float3 t = make_float3(T_ref_curr.m[3], T_ref_curr.m[7], T_ref_curr.m[11]);
-  const float3 f2 = rotate(T_ref_curr, f_curr);
-  const float bx = dot3(t, f_ref);
-  const float by = dot3(t, f2);
-  const float a0 = dot3(f_ref, f_ref);
-  const float a2 = dot3(f_ref, f2);
-  const float a1 = -a2;
-  const float a3 = dot3(make_float3(-f2.x, -f2.y, -f2.z), f2);
-  const float det = a0 * a3 - a1 * a2;
-  const float l1 = (a3 * bx - a1 * by) / det;
-  const float l2 = (-a2 * bx + a0 * by) / det;
-  const float3 xm = scaled(f_ref, l1);
-  const float3 xn = make_float3(t.x + l2 * f2.x, t.y + l2 * f2.y, t.z + l2 * f2.z);
-  return make_float3((xm.x + xn.x) / 2.0f, (xm.y + xn.y) / 2.0f, (xm.z + xn.z) / 2.0f);
-}
-
-// src/triangulation.cu:53-68
-__device__ __forceinline__ float triangulation_uncertainty(
-    const float z, const float3 f_ref, const float3 t, const float one_pix_angle)
-{
-  const float3 a = make_float3(f_ref.x * z - t.x, f_ref.y * z - t.y, f_ref.z * z - t.z);
-  const float t_norm = sqrtf(dot3(t, t));
-  const float a_norm = sqrtf(dot3(a, a));
-  const float alpha = acosf(dot3(f_ref, t) / t_norm);
-  const float beta = acosf((-dot3(a, t)) / (t_norm * a_norm));
-  const float beta_plus = beta + one_pix_angle;
-  const float gamma_plus = (float)(CUDART_PI - (double)alpha - (double)beta_plus);
-  const float z_plus = t_norm * sinf(beta_plus) / sinf(gamma_plus);
-  return z_plus - z;
-}
-
 // src/seed_update.cu:31-37
 __device__ __forceinline__ float normal_pdf(const float x, const float mu, const float sigma_sq)
 {
-  return expf(-(x - mu) * (x - mu) / (2.0f * sigma_sq)) *
-         rsqrtf((float)(2.0 * CUDART_PI * (double)sigma_sq));
+  const float d = __fadd_rn(x, -mu);
+  const float arg = __fmul_rn(__fmul_rn(d, -d), rcp_approx(__fadd_rn(sigma_sq, sigma_sq)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(arg, 1.4426950216293334961f)));   // __expf
+  return __fmul_rn(e, rsqrtf((float)(2.0 * CUDART_PI * (double)sigma_sq)));
 }
 
-// Vogiatzis-Hernandez posterior update of one seed from the matched pixel,
-// src/seed_update.cu:58-110.  Returns false (seed untouched) when the
-// triangulated point is behind the camera (:77-80) or the update is NaN
-// (:100-103).
+// Vogiatzis-Hernandez posterior update of one seed from the matched pixel: triangulation
+// (src/triangulation.cu:30-50), one-pixel uncertainty (:53-68), moment-matched Gaussian x Beta update
+// (src/seed_update.cu:58-110).  Returns false (seed untouched) when the triangulated point is behind the
+// camera (:77-80) or the update is NaN (:100-103).
 __device__ __forceinline__ bool bayes_update(
     const FilterParams &P, const int x, const int y, const float2 match, float4 &seed)
 {
   const float mu = seed.x, sigma_sq = seed.y, a = seed.z, b = seed.w;
-  const float3 f_ref = unit_bearing(P.cam, (float)x, (float)y);
-  const float3 f_match = unit_bearing(P.cam, match.x, match.y);
-  const float3 pt = triangulate_midpoint(f_ref, f_match, P.T_ref_curr);
+  const Pose &T = P.T_ref_curr;
+  const float3 t = make_float3(T.m[3], T.m[7], T.m[11]);
+  const float3 f_ref = unit_bearing_pinned(P.cam, (float)x, (float)y);
+  const float3 f_cur = unit_bearing_pinned(P.cam, match.x, match.y);
+  // f2 = R_ref_curr * f_curr (se3.cuh:111-117): per row, the y product is the plain one
+  const float3 f2 = make_float3(
+      __fmaf_rn(f_cur.z, T.m[2], __fmaf_rn(f_cur.x, T.m[0], __fmul_rn(f_cur.y, T.m[1]))),
+      __fmaf_rn(f_cur.z, T.m[6], __fmaf_rn(f_cur.x, T.m[4], __fmul_rn(f_cur.y, T.m[5]))),
+      __fmaf_rn(f_cur.z, T.m[10], __fmaf_rn(f_cur.x, T.m[8], __fmul_rn(f_cur.y, T.m[9]))));
+  // 2x2 system of triangulatenNonLin: A = [f1.f1, -f1.f2; f1.f2, -f2.f2], rhs = [t.f1, t.f2]
+  const float a2 = dot3_pinned(f_ref, f2);
+  const float a0 = dot3_pinned(f_ref, f_ref);
+  const float a3 = __fmaf_rn(-f2.z, f2.z, __fmaf_rn(f2.y, -f2.y, -__fmul_rn(f2.x, f2.x)));   // dot(-f2, f2)
+  const float inv_det = rcp_approx(__fmaf_rn(a0, a3, __fmul_rn(a2, a2)));                   // a0 a3 - a1 a2, a1 = -a2
+  const float bx = dot3_pinned(f_ref, t);
+  const float by = dot3_pinned(f2, t);
+  const float by_a2 = __fmul_rn(by, a2), bx_a2 = __fmul_rn(bx, a2);
+  const float l1 = __fmul_rn(__fmaf_rn(bx, a3, by_a2), inv_det);                            // (a3 bx - a1 by) / det
+  const float l2 = __fmul_rn(__fmaf_rn(by, a0, -bx_a2), inv_det);                           // (-a2 bx + a0 by) / det
+  // midpoint (l1 f1 + t + l2 f2) / 2
+  const float3 pt = make_float3(
+      __fmul_rn(__fmaf_rn(f_ref.x, l1, __fmaf_rn(f2.x, l2, t.x)), 0.5f),
+      __fmul_rn(__fmaf_rn(f_ref.y, l1, __fmaf_rn(f2.y, l2, t.y)), 0.5f),
+      __fmul_rn(__fmaf_rn(f_ref.z, l1, __fmaf_rn(f2.z, l2, t.z)), 0.5f));
   if(pt.z < 0.0f)
     return false;
-  const float depth = sqrtf(dot3(pt, pt));
-  const float3 t = make_float3(P.T_ref_curr.m[3], P.T_ref_curr.m[7], P.T_ref_curr.m[11]);
-  const float tau = triangulation_uncertainty(depth, f_ref, t, P.one_pix_angle);
-  const float tau_sq = tau * tau;
-  const float s_sq = (tau_sq * sigma_sq) / (tau_sq + sigma_sq);
-  const float m = s_sq * (mu / sigma_sq + depth / tau_sq);
-  float c1 = (a / (a + b)) * normal_pdf(depth, mu, sigma_sq + tau_sq);
-  float c2 = (b / (a + b)) * (1.0f / P.depth_range);
-  const float norm_const = c1 + c2;
-  c1 = c1 / norm_const;
-  c2 = c2 / norm_const;
-  const float f = c1 * ((a + 1.0f) / (a + b + 1.0f)) + c2 * (a / (a + b + 1.0f));
-  const float e = c1 * (((a + 1.0f) * (a + 2.0f)) / ((a + b + 1.0f) * (a + b + 2.0f))) +
-                  c2 * (a * (a + 1.0f) / ((a + b + 1.0f) * (a + b + 2.0f)));
-  if(isnan(c1 * m))
+  const float depth = sqrtf(__fmaf_rn(pt.z, pt.z, __fmaf_rn(pt.y, pt.y, __fmul_rn(pt.x, pt.x))));
+
+  // triangulationUncertainty: tau = z+ - z with beta+ = beta + one pixel, gamma+ = pi - alpha - beta+ (double)
+  const float t_norm = sqrtf(dot3_pinned(t, t));
+  const float3 av = make_float3(__fmaf_rn(f_ref.x, depth, -t.x), __fmaf_rn(f_ref.y, depth, -t.y),
+                                __fmaf_rn(f_ref.z, depth, -t.z));
+  const float a_norm = sqrtf(dot3_pinned(av, av));
+  const float alpha = acosf(__fmul_rn(bx, rcp_approx(t_norm)));
+  const float beta = acosf(__fmul_rn(dot3_pinned(av, t), -rcp_approx(__fmul_rn(t_norm, a_norm))));
+  const float beta_plus = __fadd_rn(beta, P.one_pix_angle);
+  const float gamma_plus = (float)(CUDART_PI - (double)alpha - (double)beta_plus);
+  const float tau = __fmaf_rn(__fmul_rn(t_norm, sinf(beta_plus)), rcp_approx(sinf(gamma_plus)), -depth);
+  const float tau_sq = __fmul_rn(tau, tau);
+
+  const float var_sum = __fadd_rn(sigma_sq, tau_sq);
+  const float s_sq = __fmul_rn(__fmul_rn(sigma_sq, tau_sq), rcp_approx(var_sum));
+  const float m = __fmul_rn(s_sq, __fmaf_rn(mu, rcp_approx(sigma_sq), __fmul_rn(depth, rcp_approx(tau_sq))));
+  const float ab = __fadd_rn(a, b);
+  const float inv_ab = rcp_approx(ab);
+  float c1 = __fmul_rn(__fmul_rn(a, inv_ab), normal_pdf(depth, mu, var_sum));
+  float c2 = __fmul_rn(__fmul_rn(b, inv_ab), rcp_approx(P.depth_range));
+  const float inv_norm = rcp_approx(__fadd_rn(c1, c2));
+  c1 = __fmul_rn(c1, inv_norm);
+  c2 = __fmul_rn(c2, inv_norm);
+  const float ab1 = __fadd_rn(ab, 1.0f), ab2 = __fadd_rn(ab, 2.0f), a1 = __fadd_rn(a, 1.0f), a_2 = __fadd_rn(a, 2.0f);
+  const float inv_ab1 = rcp_approx(ab1), inv_d = rcp_approx(__fmul_rn(ab1, ab2));
+  const float f = __fmaf_rn(c1, __fmul_rn(a1, inv_ab1), __fmul_rn(c2, __fmul_rn(a, inv_ab1)));
+  const float e = __fmaf_rn(c1, __fmul_rn(__fmul_rn(a1, a_2), inv_d), __fmul_rn(c2, __fmul_rn(__fmul_rn(a, a1), inv_d)));
+  const float c1_m = __fmul_rn(c1, m);
+  if(isnan(c1_m))
     return false;
-  const float mu_prime = c1 * m + c2 * mu;
-  seed.y = c1 * (s_sq + m * m) + c2 * (sigma_sq + mu * mu) - mu_prime * mu_prime;
+  const float mu_prime = __fmaf_rn(mu, c2, c1_m);
+  const float second = __fmaf_rn(c1, __fmaf_rn(m, m, s_sq), __fmul_rn(c2, __fmaf_rn(mu, mu, sigma_sq)));
+  seed.y = __fmaf_rn(-mu_prime, mu_prime, second);
   seed.x = mu_prime;
-  const float a_prime = (e - f) / (f - e / f);
+  const float inv_f = rcp_approx(f);
+  const float a_prime = __fmul_rn(__fadd_rn(e, -f), rcp_approx(__fmaf_rn(-e, inv_f, f)));   // (e - f) / (f - e / f)
   seed.z = a_prime;
-  seed.w = a_prime * (1.0f - f) / f;
+  seed.w = __fmul_rn(__fmul_rn(a_prime, __fadd_rn(1.0f, -f)), inv_f);
   return true;
 }
 

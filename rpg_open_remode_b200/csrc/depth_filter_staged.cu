@@ -315,7 +315,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       {
         float l = S.l_checkpoint[pix][k / L_CHECKPOINT_STEP];
         for(int t = 0; t < (k & (L_CHECKPOINT_STEP - 1)); ++t) l += RMD_EPIPOLAR_STEP;
-        const float2 px = make_float2(seg.mean.x + l * seg.dir.x, seg.mean.y + l * seg.dir.y);
+        const float2 px = candidate_px(seg.mean.x, seg.mean.y, seg.dir.x, seg.dir.y, l);
         return !candidate_rejected<PS>(px, P.width, P.height);
       };
       // l-interval in which P <= mean + l*dir < size - P holds, per axis
@@ -515,7 +515,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
           {
             float l = S.l_checkpoint[r * TILE_W + src][k / L_CHECKPOINT_STEP];
             for(int t = 0; t < (k & (L_CHECKPOINT_STEP - 1)); ++t) l += RMD_EPIPOLAR_STEP;
-            const float2 px = make_float2(R.mean_x + l * R.dir_x, R.mean_y + l * R.dir_y);
+            const float2 px = candidate_px(R.mean_x, R.mean_y, R.dir_x, R.dir_y, l);
             if(candidate_rejected<PS>(px, P.width, P.height))
               continue;
             const TapFrame frame = tap_frame<PS>(px, P.tex_quant);
@@ -695,7 +695,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       for(int i = 0; i < CHUNK; ++i, l += RMD_EPIPOLAR_STEP)
       {
         if(!(l <= R.half_len)) break;
-        const float2 px = make_float2(R.mean_x + l * R.dir_x, R.mean_y + l * R.dir_y);
+        const float2 px = candidate_px(R.mean_x, R.mean_y, R.dir_x, R.dir_y, l);
         if(candidate_rejected<PS>(px, P.width, P.height))
           continue;
         const TapFrame frame = tap_frame<PS>(px, P.tex_quant);
@@ -801,7 +801,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
         const int best_idx = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull));
         float l = S.l_checkpoint[pix][best_idx / L_CHECKPOINT_STEP];
         for(int k = 0; k < (best_idx & (L_CHECKPOINT_STEP - 1)); ++k) l += RMD_EPIPOLAR_STEP;
-        const float2 best_px = make_float2(seg.mean.x + l * seg.dir.x, seg.mean.y + l * seg.dir.y);
+        const float2 best_px = candidate_px(seg.mean.x, seg.mean.y, seg.dir.x, seg.dir.y, l);
         if(P.matches)
           P.matches[(size_t)y * P.match_stride + x] = best_px;
         if(bayes_update(P, x, y, best_px, seed))

@@ -52,8 +52,15 @@ def agreement(A, B, depth_range):
            "mu_bit_identical": float((d == 0).mean()), "mu_within_1e-3_range": float((d <= 1e-3).mean()),
            "mu_p99_over_range": float(np.percentile(d, 99)), "mu_max_over_range": float(d.max()),
            "converged_product": int((A["conv"] == 1).sum()), "converged_reference": int((B["conv"] == 1).sum())}
+    # Seeds whose posterior variance has collapsed to a rounding residue of either sign (sigma_sq <= 0 in
+    # either implementation) are "trapped": sqrtf(sigma_sq) is NaN, both report NO_MATCH and add 1 to b every
+    # frame (defined deviation 2).  WHEN a seed falls in depends on the last bit of its variance,
+    # so their b counts are compared as a population, not pixel by pixel.
+    trapped_a, trapped_b = A["sigma_sq"] <= 0, B["sigma_sq"] <= 0
+    out["trapped_product"], out["trapped_reference"] = int(trapped_a.sum()), int(trapped_b.sum())
+    live = sel & ~trapped_a & ~trapped_b
     for name, tol in (("sigma_sq", 1e-2), ("a", 1e-3), ("b", 1e-3)):
-        rel = (np.abs(A[name].astype(np.float64) - B[name]) / np.maximum(np.abs(B[name]), 1e-12))[sel]
+        rel = (np.abs(A[name].astype(np.float64) - B[name]) / np.maximum(np.abs(B[name]), 1e-12))[live]
         out[f"{name}_within_{tol:g}_rel"] = float((rel <= tol).mean())
     return out
 
@@ -137,10 +144,12 @@ def _run_full(seq, n_frames, patch, every=None):
 
 # Bars: (states equal, mu bit-identical, mu within 1e-3 range, sigma_sq/a/b within tolerance).
 # Set from the measured agreement (profiles/r02_parity_full_length.json), with margin.
+# Measured (profiles/r02_parity_full_length.json): states 99.82-99.97 %, mu bit-identical 97.4-98.1 %, mu within
+# 1e-3 range 99.6-99.8 %, sigma_sq / a / b 97.8-99.6 %, converged counts equal to 3-50 of 0.3-2.1 M pixels.
 BARS = {
-    "c2": dict(states=0.995, identical=0.80, within=0.985, params=0.97),
-    "c3": dict(states=0.995, identical=0.80, within=0.985, params=0.97),
-    "c4": dict(states=0.990, identical=0.70, within=0.980, params=0.96),
+    "c2": dict(states=0.998, identical=0.95, within=0.99, params=0.97),
+    "c3": dict(states=0.995, identical=0.95, within=0.99, params=0.96),
+    "c4": dict(states=0.995, identical=0.95, within=0.99, params=0.96),
 }
 
 
@@ -152,6 +161,7 @@ def _assert_bars(m, bars):
         assert m[k] >= bars["params"], (k, m)
     n = m["pixels"]
     assert abs(m["converged_product"] - m["converged_reference"]) <= 5e-3 * n, m
+    assert abs(m["trapped_product"] - m["trapped_reference"]) <= 5e-3 * n, m
 
 
 @pytest.mark.skipif(not rb.available(5), reason="oracle/_ref not built (needs /root/reference at build time)")

@@ -33,8 +33,11 @@ def run(cfg):
             best = tot; seg = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
     return best, seg
 
-for cfg in [(16, 512, 384, 16, 32, 100, 1), (16, 512, 384, 16, 32, 100, 2), (16, 512, 384, 16, 32, 100, 0), (16, 512, 256, 16, 48, 100, 1),
-            (16, 512, 384, 8, 32, 100, 2), (16, 512, 384, 12, 24, 100, 2), (16, 768, 384, 16, 32, 100, 2), (16, 512, 512, 16, 32, 100, 2)]:
+CONFIGS = [(16, 512, 384, 16, 32, 100, 1), (16, 256, 128, 16, 32, 100, 1), (32, 128, 64, 16, 32, 100, 1), (32, 256, 128, 16, 32, 50, 1),
+           (32, 192, 96, 16, 32, 100, 1), (16, 512, 384, 16, 32, 100, 0), (16, 512, 384, 32, 32, 100, 1), (16, 512, 384, 4, 32, 100, 1)]
+if len(sys.argv) > 1:
+    CONFIGS = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+for cfg in CONFIGS:
     tot, seg = run(cfg)
     print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d pdl %d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-199 %.2f ms" %
-          (*cfg, tot, 199 / tot * 1e3, *seg))
+          (*cfg, tot, 199 / tot * 1e3, *seg), flush=True)
