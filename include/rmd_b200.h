@@ -49,6 +49,7 @@ extern "C" {
 #define RMD_ERR_INVALID_ARGUMENT (-1)
 #define RMD_ERR_NOT_INITIALISED  (-2)  /* e.g. update before set_reference */
 #define RMD_ERR_UNSUPPORTED      (-3)
+#define RMD_ERR_DEVICE_WAIT       (-4)  /* a bounded device-side wait of a chained launch expired (a bug, not a state) */
 
 /* rmd::ConvergenceStates, include/rmd/seed_matrix.cuh:31-43 */
 enum rmd_convergence_state {
@@ -100,6 +101,10 @@ enum rmd_seeds_option {
    * (device_image.cuh:93-106) no longer holds for such buffers.  Pageable
    * buffers still take the staged path.  Default 0. */
   RMD_OPT_PINNED_INPUT = 4,
+  /* Frames per launch of rmd_seeds_update_device_batch (1..8, default 8): consecutive frames of the keyframe
+   * are chained inside ONE persistent launch -- a tile moves on to frame k+1 as soon as its own frame k is
+   * final, so frames overlap on the GPU.  Same results as one launch per frame (1). */
+  RMD_OPT_CHAIN_FRAMES = 5,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */
   RMD_OPT_TUNE_SPLIT_MAX = 10,            /* most CTAs sharing one busy tile (1 = never split; default 16) */

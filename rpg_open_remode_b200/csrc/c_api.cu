@@ -138,7 +138,7 @@ struct rmd_seeds
   float2 *matches; size_t matches_pitch;
   float *planar[6]; size_t planar_pitch;   // mu, sigma_sq, a, b, sum_templ, denom
   float *dense_tmp;                        // width*height floats, uploads/downloads
-  unsigned int *counters;                  // 2 x converged count (ping-pong) + converged seeds of retired tiles
+  unsigned int *counters;                  // converged count of frame f in [f % 3] + [3] converged seeds of retired tiles
 
   // scene / algorithm parameters (src/seed_matrix.cu:96-104)
   float min_depth, max_depth, avg_depth, depth_range, sigma_sq_max;
@@ -164,9 +164,12 @@ struct rmd_seeds
   int n_tiles, cta_slots;
   unsigned long long *tile_keys;
   unsigned int *tile_arrivals;
-  unsigned int *heavy_list[2], *light_list[2];  // work lists: this frame's / the next frame's
-  unsigned int *work_counts;   // 3 rotating slots of {heavy, light, helpers, items}
-  unsigned int *cursor;        // {next work-list entry, CTAs out of work} of the persistent staged launch
+  unsigned int *heavy_list[3], *light_list[3];  // work lists of frame f in [f % 3] (written during frame f - 1)
+  unsigned int *work_counts;   // 3 rotating slots of 8: {heavy, light, helpers, items, tiles listed, listers done, -, -}
+  unsigned int *cursor;        // STAGED_CURSOR_WORDS: work cursors, CTAs out of work, error flag (staged_maps.cuh)
+  unsigned int *chain_state;   // [n_tiles] tile_done + [1] list_ready (frame chaining, depth_filter_staged.cu)
+  StagedMaps *chain_maps;      // STAGED_BATCH_MAX descriptor sets of a chained launch (allocated on first use)
+  int chain_frames;            // frames per chained launch of rmd_seeds_update_device_batch (1 = one launch per frame)
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
@@ -209,8 +212,8 @@ int seeds_alloc(rmd_seeds *s)
     RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
   }
   RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->ext_ev, cudaEventDisableTiming));
-  RMD_CUDA_TRY(cudaMalloc(&s->counters, 3 * sizeof(unsigned int)));
-  RMD_CUDA_TRY(cudaMemset(s->counters, 0, 3 * sizeof(unsigned int)));
+  RMD_CUDA_TRY(cudaMalloc(&s->counters, 4 * sizeof(unsigned int)));
+  RMD_CUDA_TRY(cudaMemset(s->counters, 0, 4 * sizeof(unsigned int)));
   RMD_CUDA_TRY(cudaMemset2D(s->conv, s->conv_pitch, 0, sizeof(int) * (size_t)w, h));
   {
     s->n_tiles = ((w + staged::TILE_W - 1) / staged::TILE_W) * ((h + staged::TILE_H - 1) / staged::TILE_H);
@@ -226,14 +229,16 @@ int seeds_alloc(rmd_seeds *s)
     RMD_CUDA_TRY(cudaMalloc(&s->tile_keys, sizeof(unsigned long long) * (size_t)s->n_tiles * staged::NPIX));
     RMD_CUDA_TRY(cudaMalloc(&s->tile_arrivals, sizeof(unsigned int) * (size_t)s->n_tiles));
     s->tiles_x = (w + staged::TILE_W - 1) / staged::TILE_W;
-    for(int i = 0; i < 2; ++i)
+    for(int i = 0; i < 3; ++i)
     {
       RMD_CUDA_TRY(cudaMalloc(&s->heavy_list[i], sizeof(unsigned int) * (size_t)(s->n_tiles + staged::HELPER_CAP)));
       RMD_CUDA_TRY(cudaMalloc(&s->light_list[i], sizeof(unsigned int) * (size_t)s->n_tiles));
     }
-    RMD_CUDA_TRY(cudaMalloc(&s->work_counts, 12 * sizeof(unsigned int)));
-    RMD_CUDA_TRY(cudaMalloc(&s->cursor, 2 * sizeof(unsigned int)));
-    RMD_CUDA_TRY(cudaMemset(s->cursor, 0, 2 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMalloc(&s->work_counts, 24 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMalloc(&s->cursor, STAGED_CURSOR_WORDS * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMemset(s->cursor, 0, STAGED_CURSOR_WORDS * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMalloc(&s->chain_state, sizeof(unsigned int) * (size_t)(s->n_tiles + 1)));
+    RMD_CUDA_TRY(cudaMemset(s->chain_state, 0, sizeof(unsigned int) * (size_t)(s->n_tiles + 1)));
   }
   RMD_CUDA_TRY(cudaEventCreate(&s->t0));
   RMD_CUDA_TRY(cudaEventCreate(&s->t1));
@@ -260,9 +265,11 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->counters);
   cudaFree(s->timeline);
   cudaFree(s->tile_keys); cudaFree(s->tile_arrivals);
-  cudaFree(s->heavy_list[0]); cudaFree(s->heavy_list[1]); cudaFree(s->light_list[0]); cudaFree(s->light_list[1]);
+  for(int i = 0; i < 3; ++i) { cudaFree(s->heavy_list[i]); cudaFree(s->light_list[i]); }
   cudaFree(s->work_counts);
   cudaFree(s->cursor);
+  cudaFree(s->chain_state);
+  delete[] s->chain_maps;
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
@@ -332,11 +339,12 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   ip.conv = s->conv; ip.conv_stride = (int)(s->conv_pitch / sizeof(int));
   ip.avg_depth = s->avg_depth; ip.sigma_sq_max = s->sigma_sq_max;
   RMD_CUDA_TRY(launch_seed_init(ip, s->patch, s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->counters, 0, 3 * sizeof(unsigned int), s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned int), s->stream));
   // the first staged frame of a keyframe starts from the full work list; keys hold "no match"
   s->worklist_valid = false;
   RMD_CUDA_TRY(cudaMemsetAsync(s->tile_arrivals, 0, sizeof(unsigned int) * (size_t)s->n_tiles, s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->cursor, 0, 2 * sizeof(unsigned int), s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->cursor, 0, STAGED_CURSOR_WORDS * sizeof(unsigned int), s->stream));
+  RMD_CUDA_TRY(cudaMemsetAsync(s->chain_state, 0, sizeof(unsigned int) * (size_t)(s->n_tiles + 1), s->stream));   // frame numbering restarts
   RMD_CUDA_TRY(launch_fill_u64(s->tile_keys, (size_t)s->n_tiles * staged::NPIX, 0x407FFFFF00000000ull, s->stream));
   s->n_total += 1;
   s->n_total += 1;
@@ -350,7 +358,8 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
 // Host side of one update: pose chain, parameter block, TMA descriptors and -- when the keyframe's work
 // list is not valid (first frame, state upload, variant switch) -- its rebuild on the handle's stream.
 // Nothing is launched for the frame itself; `P` is ready for launch_depth_filter_*.
-int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const float *T_curr_world, FilterParams &P)
+int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const float *T_curr_world, FilterParams &P,
+                   StagedMaps *maps = NULL)
 {
   const Pose T_curr_ref = pose_compose(pose_from(T_curr_world), s->T_world_ref);  // seed_matrix.cu:124
   const float tx = T_curr_ref.m[3], ty = T_curr_ref.m[7], tz = T_curr_ref.m[11];
@@ -382,8 +391,8 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   P.one_pix_angle = s->one_pix_angle;
   P.tex_quant = s->tex_frac_bits > 0 ? (float)(1 << s->tex_frac_bits) : 0.0f;
   P.trust_conv = s->trust_conv ? 1 : 0;
-  P.converged_now = s->counters + (s->frame_index & 1);
-  P.converged_next = s->counters + ((s->frame_index + 1) & 1);
+  P.converged_now = s->counters + (s->frame_index % 3);
+  P.converged_next = s->counters + ((s->frame_index + 1) % 3);
   P.timeline = s->timeline;
   {
     const uint64_t f = s->frame_index;
@@ -394,26 +403,29 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.tile_arrivals = s->tile_arrivals;
     P.n_tiles = s->n_tiles; P.tiles_x = s->tiles_x; P.helper_cap = staged::HELPER_CAP;
     P.heavy_min_items = s->tune[4]; P.split_avg_pct = s->tune[5]; P.pdl = s->tune[6];
-    P.heavy_cur = s->heavy_list[(f + 1) & 1]; P.heavy_next = s->heavy_list[f & 1];
-    P.light_cur = s->light_list[(f + 1) & 1]; P.light_next = s->light_list[f & 1];
-    P.counts_cur = s->work_counts + 4 * ((f + 2) % 3);
-    P.counts_next = s->work_counts + 4 * (f % 3);
-    P.counts_zero = s->work_counts + 4 * ((f + 1) % 3);
-    P.retired_converged = s->counters + 2;
+    P.heavy_cur = s->heavy_list[f % 3]; P.heavy_next = s->heavy_list[(f + 1) % 3];
+    P.light_cur = s->light_list[f % 3]; P.light_next = s->light_list[(f + 1) % 3];
+    P.counts_cur = s->work_counts + 8 * (f % 3);
+    P.counts_next = s->work_counts + 8 * ((f + 1) % 3);
+    P.counts_zero = s->work_counts + 8 * ((f + 2) % 3);
+    P.retired_converged = s->counters + 3;
+    P.frame_no = (unsigned int)f;
+    P.tile_done = s->chain_state;
+    P.list_ready = s->chain_state + s->n_tiles;
   }
   if(s->variant == 0)
   {
     if(!s->maps) s->maps = new StagedMaps();
     {
       ProfScope prof(3);
-      const int rc = s->maps->encode(P, s->patch);
+      const int rc = (maps ? maps : s->maps)->encode(P, s->patch);
       if(rc) return rc;
     }
     if(!s->worklist_valid)
     {
       // every tile once, in image order, no helpers; nothing retired yet
-      RMD_CUDA_TRY(cudaMemsetAsync(s->work_counts, 0, 12 * sizeof(unsigned int), s->stream));
-      RMD_CUDA_TRY(cudaMemsetAsync(s->counters + 2, 0, sizeof(unsigned int), s->stream));
+      RMD_CUDA_TRY(cudaMemsetAsync(s->work_counts, 0, 24 * sizeof(unsigned int), s->stream));
+      RMD_CUDA_TRY(cudaMemsetAsync(s->counters + 3, 0, sizeof(unsigned int), s->stream));
       RMD_CUDA_TRY(launch_worklist_init(const_cast<unsigned int*>(P.light_cur),
                                         const_cast<unsigned int*>(P.counts_cur), s->n_tiles, s->stream));
       s->worklist_valid = true;
@@ -447,7 +459,7 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     ProfScope prof_launch(4);
     const FilterParams *pp = &P;
     const StagedMaps *mm = s->maps;
-    RMD_CUDA_TRY(launch_depth_filter_staged(&pp, &mm, 1, s->cursor, s->patch, s->stream));
+    RMD_CUDA_TRY(launch_depth_filter_staged(&pp, &mm, 1, 0, s->cursor, s->patch, s->stream));
   }
   else
   {
@@ -620,6 +632,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
   s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT; s->tune[6] = 1;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
+  s->chain_frames = STAGED_BATCH_MAX;
   const int rc = seeds_alloc(s);
   if(rc)
   {
@@ -663,6 +676,10 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   {
   case RMD_OPT_RECORD_MATCHES: s->record_matches = (value != 0); return 0;
   case RMD_OPT_PINNED_INPUT: s->pinned_input = (value != 0); return 0;
+  case RMD_OPT_CHAIN_FRAMES:
+    RMD_REQUIRE(value >= 1 && value <= STAGED_BATCH_MAX, "RMD_OPT_CHAIN_FRAMES: 1..8");
+    s->chain_frames = value;
+    return 0;
   case RMD_OPT_KERNEL_VARIANT:
     RMD_REQUIRE(value == 0 || value == 1, "RMD_OPT_KERNEL_VARIANT: 0 (staged) or 1 (direct)");
     s->variant = value;
@@ -832,7 +849,7 @@ int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t
     }
     {
       ProfScope prof_launch(4);
-      RMD_CUDA_TRY(launch_depth_filter_staged(pp, mm, m, h0->cursor, h0->patch, h0->stream));
+      RMD_CUDA_TRY(launch_depth_filter_staged(pp, mm, m, 0, h0->cursor, h0->patch, h0->stream));
     }
     for(int k = 0; k < m; ++k)
       finish_update(handles[batch_ids[g + k]]);
@@ -1043,12 +1060,40 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
   if(!s->has_reference)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_device_batch: set_reference has not been called");
   DeviceGuard guard(s->device);
-  for(int i = 0; i < n_frames; ++i)
+  const char *base = reinterpret_cast<const char*>(dev_frames);
+  // Frame chaining: up to STAGED_BATCH_MAX consecutive frames per launch of the staged kernel.  Every tile
+  // walks through the frames of a launch on its own (frame k+1 of a tile only needs frame k of that tile), so
+  // frames overlap on the GPU and the per-frame launch gap disappears; results are those of one launch per frame.
+  const int per_launch = (s->variant == 0 && !s->timeline && !s->timing) ? s->chain_frames : 1;
+  for(int i = 0; i < n_frames; )
   {
-    const float *frame = reinterpret_cast<const float*>(
-        reinterpret_cast<const char*>(dev_frames) + (size_t)i * frame_stride_bytes);
-    const int rc = enqueue_update(s, frame, pitch_bytes, T_curr_world + 12 * i);
-    if(rc) return rc;
+    const int m = (n_frames - i < per_launch) ? n_frames - i : per_launch;
+    if(m <= 1)
+    {
+      const int rc = enqueue_update(s, reinterpret_cast<const float*>(base + (size_t)i * frame_stride_bytes), pitch_bytes,
+                                    T_curr_world + 12 * i);
+      if(rc) return rc;
+      i += 1;
+      continue;
+    }
+    if(!s->chain_maps) s->chain_maps = new StagedMaps[STAGED_BATCH_MAX];
+    FilterParams P[STAGED_BATCH_MAX];
+    const FilterParams *pp[STAGED_BATCH_MAX];
+    const StagedMaps *mm[STAGED_BATCH_MAX];
+    for(int k = 0; k < m; ++k)
+    {
+      const int rc = prepare_update(s, reinterpret_cast<const float*>(base + (size_t)(i + k) * frame_stride_bytes),
+                                    pitch_bytes, T_curr_world + 12 * (i + k), P[k], &s->chain_maps[k]);
+      if(rc) return rc;
+      pp[k] = &P[k];
+      mm[k] = &s->chain_maps[k];
+    }
+    RMD_CUDA_TRY(launch_depth_filter_staged(pp, mm, m, 1, s->cursor, s->patch, s->stream));
+    for(int k = 0; k < m; ++k)
+      finish_update(s);
+    s->n_fused -= (uint64_t)(m - 1);   // launch counters count launches, not frames
+    s->n_total -= (uint64_t)(m - 1);
+    i += m;
   }
   return 0;
 }
@@ -1059,6 +1104,10 @@ int rmd_seeds_sync(rmd_seeds_t *s)
   DeviceGuard guard(s->device);
   RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  unsigned int flag = 0u;
+  RMD_CUDA_TRY(cudaMemcpy(&flag, s->cursor + STAGED_BATCH_MAX + 1, sizeof(flag), cudaMemcpyDeviceToHost));
+  if(flag)
+    return fail(RMD_ERR_DEVICE_WAIT, "rmd_seeds_sync: a bounded wait of a chained launch expired on the device");
   return 0;
 }
 
@@ -1209,14 +1258,14 @@ int rmd_seeds_converged_count(rmd_seeds_t *s, size_t *count)
 {
   RMD_REQUIRE(s && count, "rmd_seeds_converged_count: null argument");
   DeviceGuard guard(s->device);
-  unsigned int v[3] = {0u, 0u, 0u};
+  unsigned int v[4] = {0u, 0u, 0u, 0u};
   if(s->frame_index > 0)
   {
     RMD_CUDA_TRY(cudaMemcpyAsync(v, s->counters, sizeof(v), cudaMemcpyDeviceToHost, s->stream));
     RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   }
-  // seeds of tiles the staged kernel has retired from its work list are counted in v[2]
-  *count = (size_t)v[s->frame_index & 1] + (s->last_staged ? (size_t)v[2] : 0);
+  // seeds of tiles the staged kernel has retired from its work list are counted in v[3]
+  *count = (size_t)v[s->frame_index % 3] + (s->last_staged ? (size_t)v[3] : 0);
   return 0;
 }
 

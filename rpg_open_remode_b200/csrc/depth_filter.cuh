@@ -31,7 +31,11 @@ struct StagedMaps;
 // One launch for n keyframes (n = 1: the single-keyframe instantiation).  Persistent grid: one CTA per
 // resident slot, each pulling entries of the keyframes' work lists through `cursor` (2 zero-initialised
 // uints owned by the caller; the kernel leaves them at zero).
-cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const StagedMaps *const *maps, int n,
+// chain = 0: P[0..n) are n keyframes updated by the same frame.  chain = 1: P[0..n) are n CONSECUTIVE FRAMES of
+// one keyframe; a tile moves on to frame k+1 as soon as its own frame k is final (FilterParams::tile_done), so
+// frames overlap on the GPU and the launch gap between frames disappears.  `cursor`: STAGED_CURSOR_WORDS
+// zero-initialised uints (staged_maps.cuh).
+cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const StagedMaps *const *maps, int n, int chain,
                                        unsigned int *cursor, int patch_side, cudaStream_t stream);
 // Resident CTAs of the staged kernel on the current device (SMs x occupancy), 0 on error.
 int staged_cta_slots(int patch_side);

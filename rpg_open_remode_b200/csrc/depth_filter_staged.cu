@@ -84,6 +84,7 @@ struct __align__(128) StagedSmem
   int strip_ox, strip_oy, strip_w, strip_rows;
   int is_last;
   unsigned int fetch;                  // index of the work-list entry this CTA processes next (persistent loop)
+  unsigned int fetch_heavy, fetch_light;  // chain mode: the frame's list sizes, read BEFORE the index was drawn
   int items_acc;                       // work items of the tile (sum of the seeds' chunk counts)
   unsigned int row_active[TILE_H];     // ballot of the seeds to update, per pixel row
   unsigned long long mbar;
@@ -156,6 +157,45 @@ struct StripTaps
   __device__ __forceinline__ float at(const int j, const int i) const { return origin[j * stride + i]; }
 };
 
+// ---- frame chaining: release / acquire on global flags, bounded waits
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void st_release(unsigned int *p, const unsigned int v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Waits until *p >= want.  Bounded (~0.2 s): whatever is waited for has already been picked by a resident
+// CTA, so the bound is never reached in a correct run; if it is, the launch reports it instead of hanging.
+__device__ __forceinline__ bool wait_at_least(const unsigned int *p, const unsigned int want)
+{
+  for(unsigned int it = 0; it < (1u << 22); ++it)
+  {
+    if(ld_acquire(p) >= want)
+      return true;
+    __nanosleep(32);
+  }
+  return false;
+}
+
+// A lead CTA has appended its tile's entries to the next frame's work list (or retired the tile): when
+// every tile listed in THIS frame has done so, the next frame's list is complete.
+__device__ __forceinline__ void signal_listed(const FilterParams &P)
+{
+  __threadfence();            // my entries are written before I count myself ...
+  const unsigned int done = atomicAdd(P.counts_next + 5, 1u) + 1u;
+  if(done == __ldcg(P.counts_cur + 4))
+  {
+    __threadfence();          // ... and everybody's (observed through the counter) before the list is published
+    atomicMax(P.list_ready, P.frame_no + 1u);
+  }
+}
+
 __device__ __forceinline__ int to_int_clamped(float v)
 {
   return (int)fminf(fmaxf(v, -1.0e6f), 1.0e6f);  // NaN -> -1e6 (fmaxf drops NaN)
@@ -167,7 +207,8 @@ __device__ __forceinline__ int to_int_clamped(float v)
 // `mbar_phase` is the parity of the CTA's TMA mbarrier, carried from tile to tile.
 template<int PS>
 __device__ __forceinline__ void process_tile(const FilterParams &P, const StagedTensorMaps &M, StagedSmem<PS> &S,
-                                             const unsigned int entry, unsigned int &mbar_phase)
+                                             const unsigned int entry, unsigned int &mbar_phase,
+                                             const bool chain, const bool wait_prev, unsigned int *error_flag)
 {
   const int lane = threadIdx.x, wid = threadIdx.y;   // warp `wid` owns pixel row `wid` of the tile
   const int tid = wid * TILE_W + lane;
@@ -182,6 +223,14 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
   const int x0 = (tile % P.tiles_x) * TILE_W, y0 = (tile / P.tiles_x) * TILE_H;
   const int x = x0 + lane, y = y0 + wid;
   const bool lead = (z == 0);  // the CTA that records what all of them compute identically
+  if(wait_prev)
+  {
+    // chain mode, not the launch's first frame: this tile's seeds are final once the previous frame's
+    // finaliser has released them (pixels never interact: frame f of a tile depends on frame f-1 of that tile only)
+    if(tid == 0 && !wait_at_least(P.tile_done + tile, P.frame_no - 1u))
+      atomicExch(error_flag, 1u);
+    __syncthreads();
+  }
 
   // debug timeline (RMD_OPT_DEBUG_TIMELINE), lead CTA only:
   // [0] globaltimer ns at start, [1..4] SM cycles since start after classification /
@@ -216,8 +265,9 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
   {
     conv_ptr = P.conv + (size_t)y * P.conv_stride + x;
     seed_ptr = P.seed + (size_t)y * P.seed_stride + x;
-    prev = *conv_ptr;
-    seed = *seed_ptr;   // issued with the state load, not after it: one memory round trip for the tile
+    // (L2 loads: in chain mode the previous frame's finaliser may have run on another SM during this launch)
+    prev = __ldcg(conv_ptr);
+    seed = __ldcg(seed_ptr);   // issued with the state load, not after it: one memory round trip for the tile
     if(P.trust_conv && (prev == RMD_BORDER || prev == RMD_CONVERGED || prev == RMD_DIVERGED))
     {
       state = prev;
@@ -257,7 +307,19 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       if(lane == 0 && conv_ballot)
         atomicAdd(any_pending ? P.converged_now : P.retired_converged, (unsigned int)__popc(conv_ballot));
       if(tid == 0 && any_pending)
+      {
         P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
+        atomicAdd(P.counts_next + 4, 1u);
+      }
+      if(chain)
+      {
+        if(tid == 0)
+          signal_listed(P);
+        __threadfence();        // the state changes written above (conv of newly absorbing seeds) ...
+        __syncthreads();
+        if(tid == 0)
+          st_release(P.tile_done + tile, P.frame_no);   // ... are visible before the tile is released
+      }
     }
     if(stamps && tid == 0) stamps[1] = -(clock64() - stamp_t0);
     return;
@@ -449,14 +511,15 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     // this tile's entries in the NEXT frame's work list
     const int items = S.items_acc;
     atomicAdd(P.counts_next + 3, (unsigned int)items);
-    const unsigned int avg_per_slot = P.counts_cur[3] / (unsigned int)P.cta_slots;
+    const unsigned int frame_items = __ldcg(P.counts_cur + 3);   // (chain mode: still growing -- a heuristic input only)
+    const unsigned int avg_per_slot = frame_items / (unsigned int)P.cta_slots;
     // CTAs in proportion to the tile's share of the frame: about one resident-CTA
     // slot's worth of items each (never fewer than split_items_per_cta, the fixed
     // cost of a CTA must pay off), so the frame's CTAs finish together and the sum
     // of all helpers stays below the number of slots.
     // (no estimate of the frame's total in the first frame of a keyframe: no split)
     int znext = 1;
-    if(P.split_max > 1 && items > P.split_min_items && P.counts_cur[3] != 0u)
+    if(P.split_max > 1 && items > P.split_min_items && frame_items != 0u)
     {
       const unsigned int target = max((unsigned int)P.split_items_per_cta, avg_per_slot * (unsigned int)P.split_avg_pct / 100u);
       znext = (int)min((unsigned int)P.split_max, ((unsigned int)items + target - 1u) / target);
@@ -476,6 +539,9 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     {
       P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
     }
+    atomicAdd(P.counts_next + 4, 1u);
+    if(chain)
+      signal_listed(P);
     if(stamps) { stamps[7] = S.items_acc; stamps[12] = n_active; }
   }
 
@@ -816,6 +882,13 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     if(state != prev)
       *conv_ptr = state;
   }
+  if(chain)
+  {
+    __threadfence();            // seeds and states of this frame ...
+    __syncthreads();
+    if(tid == 0)
+      st_release(P.tile_done + tile, P.frame_no);   // ... are visible before the next frame may read them
+  }
   RMD_STAMP(5);
 }
 #undef RMD_STAMP
@@ -845,28 +918,77 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int n_kf = (K == 1) ? 1 : B.n;
   const int tid = threadIdx.y * TILE_W + threadIdx.x;
-  if(blockIdx.x == 0 && tid == 0)
+  if(blockIdx.x == 0 && tid == 0 && !((K > 1) && (B.chain != 0)))
   {
     for(int k = 0; k < n_kf; ++k)
     {
       const FilterParams &P = B.p[K == 1 ? 0 : k];
       *P.converged_next = 0u;
-      P.counts_zero[0] = 0u; P.counts_zero[1] = 0u; P.counts_zero[2] = 0u; P.counts_zero[3] = 0u;
+#pragma unroll
+      for(int w = 0; w < 6; ++w) P.counts_zero[w] = 0u;
     }
   }
   if(tid == 0)
     mbar_init(&S.mbar, 1);
   unsigned int mbar_phase = 0u;
+  const bool chain = (K > 1) && (B.chain != 0);
+  unsigned int *const error_flag = B.cursor + STAGED_BATCH_MAX + 1;
+  int g = 0;           // chain mode: frame of the launch this CTA is working on
   for(;;)
   {
     if(tid == 0)
-      S.fetch = atomicAdd(B.cursor, 1u);
+    {
+      if(chain)
+      {
+        const FilterParams &P = B.p[K == 1 ? 0 : g];
+        // frame g's work list is written by the lead CTAs of frame g-1, in this launch
+        if(g > 0 && !wait_at_least(P.list_ready, P.frame_no))
+          atomicExch(error_flag, 1u);
+        // The sizes are read BEFORE the index is drawn: the slot is recycled (zeroed) by the first CTA
+        // that finds this frame's cursor exhausted, i.e. after every valid index has been drawn.
+        S.fetch_heavy = __ldcg(P.counts_cur + 0);
+        S.fetch_light = __ldcg(P.counts_cur + 1);
+        __threadfence();
+      }
+      S.fetch = atomicAdd(B.cursor + (chain ? g : 0), 1u);
+    }
     __syncthreads();   // also: everybody is done with the previous tile's shared memory (and sees the mbarrier)
     const unsigned int i = S.fetch;
-    // entry i of the concatenation: heavy lists of keyframes 0..n-1, then their light lists
     int kf = -1;
     unsigned int entry = 0u;
+    if(chain)
     {
+      const FilterParams &P = B.p[K == 1 ? 0 : g];
+      const unsigned int n_heavy = S.fetch_heavy, n_light = S.fetch_light;
+      if(i < n_heavy) { kf = g; entry = __ldcg(P.heavy_cur + i); }
+      else if(i - n_heavy < n_light) { kf = g; entry = __ldcg(P.light_cur + (i - n_heavy)); }
+      if(i == 0u && tid == 0)
+      {
+        // whoever starts a frame clears what the NEXT frame will accumulate into (nobody uses those slots
+        // any more: their last readers were the lead CTAs of frame g-1, which all finished listing before
+        // this frame's list was complete)
+        *P.converged_next = 0u;
+#pragma unroll
+        for(int w = 0; w < 6; ++w) P.counts_zero[w] = 0u;
+        if(__ldcg(P.counts_cur + 4) == 0u)
+        {
+          // nothing listed (every tile has retired): no lead CTA will publish the next frame's (empty) list
+          __threadfence();
+          atomicMax(P.list_ready, P.frame_no + 1u);
+        }
+      }
+      if(kf < 0)
+      {
+        g += 1;          // this frame's list is exhausted: on to the next one
+        if(g >= n_kf)
+          break;
+        __syncthreads();   // S.fetch is rewritten next
+        continue;
+      }
+    }
+    else
+    {
+      // entry i of the concatenation: heavy lists of keyframes 0..n-1, then their light lists
       unsigned int base = 0u;
 #pragma unroll 1
       for(int k = 0; k < n_kf && kf < 0; ++k)
@@ -884,21 +1006,21 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
         if(i - base < n_light) { kf = k; entry = P.light_cur[i - base]; }
         base += n_light;
       }
+      if(kf < 0)
+        break;           // the lists are exhausted (uniform: every thread read the same index)
     }
-    if(kf < 0)
-      break;           // the lists are exhausted (uniform: every thread read the same index)
-    process_tile<PS>(B.p[K == 1 ? 0 : kf], B.m[K == 1 ? 0 : kf], S, entry, mbar_phase);
+    process_tile<PS>(B.p[K == 1 ? 0 : kf], B.m[K == 1 ? 0 : kf], S, entry, mbar_phase, chain, chain && g > 0, error_flag);
     __syncthreads();   // S.fetch and the tile's shared state are free again
   }
   // the last CTA out rewinds the cursor for the next launch (launches on a stream are ordered)
   if(tid == 0)
   {
     __threadfence();
-    const unsigned int done = atomicAdd(B.cursor + 1, 1u);
+    const unsigned int done = atomicAdd(B.cursor + STAGED_BATCH_MAX, 1u);
     if(done == gridDim.x - 1u)
     {
-      B.cursor[0] = 0u;
-      B.cursor[1] = 0u;
+#pragma unroll
+      for(int w = 0; w <= STAGED_BATCH_MAX; ++w) B.cursor[w] = 0u;
     }
   }
 }
@@ -1017,7 +1139,7 @@ struct StagedLaunch
     return cached[device];
   }
 
-  static cudaError_t launch(const FilterParams *const *P, const StagedMaps *const *maps, int n,
+  static cudaError_t launch(const FilterParams *const *P, const StagedMaps *const *maps, int n, int chain,
                             unsigned int *cursor, cudaStream_t stream)
   {
     int device = 0;
@@ -1041,6 +1163,9 @@ struct StagedLaunch
     }
     B.cursor = cursor;
     B.n = n;
+    B.chain = chain;
+    if(chain)
+      tiles = P[0]->n_tiles + P[0]->helper_cap;   // the frames of a chain share the CTAs
     const dim3 block(TILE_W, NWARPS);
     const dim3 grid(std::min(n_slots, tiles));   // persistent: never more CTAs than can be resident
     cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
@@ -1055,20 +1180,20 @@ struct StagedLaunch
 
 } // namespace
 
-cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const StagedMaps *const *maps, int n,
+cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const StagedMaps *const *maps, int n, int chain,
                                        unsigned int *cursor, int patch_side, cudaStream_t stream)
 {
   if(n < 1 || n > STAGED_BATCH_MAX || !P || !maps || !cursor)
     return cudaErrorInvalidValue;
   // RMD_FORCE_BATCH_KERNEL=1 (test hook): single keyframes also go through the batched instantiation
   static const bool force_batch = (getenv("RMD_FORCE_BATCH_KERNEL") != NULL);
-  const bool single = (n == 1) && !force_batch;
+  const bool single = (n == 1) && !force_batch && !chain;
   if(patch_side == 5)
-    return single ? StagedLaunch<5, 1>::launch(P, maps, n, cursor, stream)
-                  : StagedLaunch<5, STAGED_BATCH_MAX>::launch(P, maps, n, cursor, stream);
+    return single ? StagedLaunch<5, 1>::launch(P, maps, n, 0, cursor, stream)
+                  : StagedLaunch<5, STAGED_BATCH_MAX>::launch(P, maps, n, chain, cursor, stream);
   if(patch_side == 7)
-    return single ? StagedLaunch<7, 1>::launch(P, maps, n, cursor, stream)
-                  : StagedLaunch<7, STAGED_BATCH_MAX>::launch(P, maps, n, cursor, stream);
+    return single ? StagedLaunch<7, 1>::launch(P, maps, n, 0, cursor, stream)
+                  : StagedLaunch<7, STAGED_BATCH_MAX>::launch(P, maps, n, chain, cursor, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -118,11 +118,16 @@ struct FilterParams
   // are counted once in *retired_converged).
   const unsigned int *heavy_cur, *light_cur;
   unsigned int *heavy_next, *light_next;
-  // {heavy entries, light entries, helper entries reserved, work items of the frame}
+  // {heavy entries, light entries, helper entries reserved, work items of the frame, tiles listed (lead
+  //  entries), lead CTAs of the previous frame that have finished listing, -, -}: 8 uints per frame
   const unsigned int *counts_cur;
   unsigned int *counts_next, *counts_zero;
   unsigned int *retired_converged;
   int helper_cap;                        // most helper entries per frame
+  // Frame chaining (several consecutive frames of one keyframe in ONE launch, depth_filter_staged.cu):
+  unsigned int frame_no;                 // updates since set_reference, 1, 2, ...
+  unsigned int *tile_done;               // [tiles] frame_no of the last frame that finalised the tile
+  unsigned int *list_ready;              // highest frame_no whose work list is complete
 };
 
 } // namespace rmdb

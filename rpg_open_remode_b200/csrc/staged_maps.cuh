@@ -62,11 +62,15 @@ struct alignas(64) StagedBatch
 {
   StagedTensorMaps m[K];
   FilterParams p[K];
-  // cursor[0]: next entry of the concatenated work lists (all heavy lists, then all light lists);
-  // cursor[1]: CTAs that have run out of work.  The last CTA out leaves both at zero.
+  // cursor[g], g < STAGED_BATCH_MAX: next entry of the work list(s) -- batch mode uses cursor[0] over the
+  // concatenation (all heavy lists, then all light lists), chain mode one cursor per frame;
+  // cursor[STAGED_BATCH_MAX]: CTAs that have run out of work; cursor[STAGED_BATCH_MAX + 1]: error flag
+  // (a bounded wait of the chain mode expired).  The last CTA out leaves the cursors and the count at zero.
   unsigned int *cursor;
-  int n;                 // keyframes in this launch, 1 <= n <= K
+  int n;                 // keyframes (batch) or consecutive frames (chain) in this launch, 1 <= n <= K
+  int chain;             // 0: p[0..n) = n keyframes updated by one frame; 1: p[0..n) = n consecutive frames of one keyframe
 };
+constexpr int STAGED_CURSOR_WORDS = STAGED_BATCH_MAX + 2;
 
 // Tiled 2-D tensor maps (cuTensorMapEncodeTiled) over the pitched reference
 // and current images.  Box shapes are fixed when a map is encoded; the box

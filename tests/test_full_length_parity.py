@@ -114,11 +114,22 @@ def test_device_resident_path_equals_host_path(patch, size):
     single.setReferenceImageDevice(dense[0].data_ptr(), W * 4, poses[0], dmin, dmax)
     for k in range(1, N):
         single.updateDevice(dense[k].data_ptr(), W * 4, poses[k])
-    for name, g in (("updateDeviceBatch", batch), ("updateDevice", single)):
+    # the same with 3 frames and with 1 frame per chained launch (RMD_OPT_CHAIN_FRAMES; default 8)
+    others = []
+    for frames_per_launch in (3, 1):
+        g = rmd.SeedMatrix(W, H, cam, patch_side=patch)
+        g.setOption(rmd.OPT_CHAIN_FRAMES, frames_per_launch)
+        g.setReferenceImageDevice(dense[0].data_ptr(), W * 4, poses[0], dmin, dmax)
+        g.updateDeviceBatch(dense[1].data_ptr(), W * H * 4, W * 4, poses[1:20])      # two calls: chains restart cleanly
+        g.updateDeviceBatch(dense[20].data_ptr(), W * H * 4, W * 4, poses[20:])
+        others.append(("chain of %d" % frames_per_launch, g))
+    for name, g in [("updateDeviceBatch", batch), ("updateDevice", single)] + others:
         got = _snap(g)
         for field in ("conv", "mu", "sigma_sq", "a", "b"):
             assert np.array_equal(got[field], want[field]), f"{name}: {field} differs from the host path"
         assert g.getConvergedCount() == host.getConvergedCount()
+        g.sync()      # also reports an expired device-side wait of a chained launch
+    assert batch.launchCount()[0] == (N - 1 + 7) // 8 and single.launchCount()[0] == N - 1
     torch.cuda.synchronize()
 
 
