@@ -113,7 +113,8 @@ enum rmd_seeds_option {
   RMD_OPT_TUNE_SPARSE_MAX_SEEDS = 13,     /* tiles with at most this many seeds to update skip TMA staging (16; 0 = off) */
   RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14,      /* tiles with at least this many items are dispatched first (32) */
   RMD_OPT_TUNE_SPLIT_AVG_PCT = 15,        /* target items per CTA of a split tile, in % of the frame's items per resident CTA slot (100) */
-  RMD_OPT_TUNE_PDL = 16            /* 1 (default): programmatic dependent launch of consecutive frames */
+  RMD_OPT_TUNE_PDL = 16,           /* 1 (default): programmatic dependent launch of consecutive frames */
+  RMD_OPT_TUNE_WARP_TILE_SEEDS = 17 /* tiles with at most this many seeds to update (and a few dozen candidates) are processed by one warp, eight per CTA (8; 0 = off) */
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

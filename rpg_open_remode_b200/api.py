@@ -40,6 +40,7 @@ OPT_CHAIN_FRAMES = 5
 # tuning knobs of the staged kernel (include/rmd_b200.h RMD_OPT_TUNE_*; results never depend on them)
 (OPT_TUNE_SPLIT_MAX, OPT_TUNE_SPLIT_MIN_ITEMS, OPT_TUNE_SPLIT_ITEMS_PER_CTA, OPT_TUNE_SPARSE_MAX_SEEDS,
  OPT_TUNE_HEAVY_MIN_ITEMS, OPT_TUNE_SPLIT_AVG_PCT, OPT_TUNE_PDL) = 10, 11, 12, 13, 14, 15, 16
+OPT_TUNE_WARP_TILE_SEEDS = 17
 FIELD_DEBUG_TIMELINE = 100
 VARIANT_STAGED, VARIANT_DIRECT = 0, 1
 

@@ -164,7 +164,7 @@ struct rmd_seeds
   int n_tiles, cta_slots;
   unsigned long long *tile_keys;
   unsigned int *tile_arrivals;
-  unsigned int *heavy_list[3], *light_list[3];  // work lists of frame f in [f % 3] (written during frame f - 1)
+  unsigned int *heavy_list[3], *light_list[3], *sparse_list[3];  // work lists of frame f in [f % 3] (written during frame f - 1)
   unsigned int *work_counts;   // 3 rotating slots of 8: {heavy, light, helpers, items, tiles listed, listers done, -, -}
   unsigned int *cursor;        // STAGED_CURSOR_WORDS: work cursors, CTAs out of work, error flag (staged_maps.cuh)
   unsigned int *chain_state;   // [n_tiles] tile_done + [1] list_ready (frame chaining, depth_filter_staged.cu)
@@ -173,7 +173,7 @@ struct rmd_seeds
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  int tune[7];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl
+  int tune[8];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
   // lens undistortion of 8-bit frames (ingest.cuh); maps are null until init_undistortion_map
   short2 *undist_xy; uint16_t *undist_frac;
@@ -233,6 +233,7 @@ int seeds_alloc(rmd_seeds *s)
     {
       RMD_CUDA_TRY(cudaMalloc(&s->heavy_list[i], sizeof(unsigned int) * (size_t)(s->n_tiles + staged::HELPER_CAP)));
       RMD_CUDA_TRY(cudaMalloc(&s->light_list[i], sizeof(unsigned int) * (size_t)s->n_tiles));
+      RMD_CUDA_TRY(cudaMalloc(&s->sparse_list[i], sizeof(unsigned int) * (size_t)s->n_tiles));
     }
     RMD_CUDA_TRY(cudaMalloc(&s->work_counts, 24 * sizeof(unsigned int)));
     RMD_CUDA_TRY(cudaMalloc(&s->cursor, STAGED_CURSOR_WORDS * sizeof(unsigned int)));
@@ -265,7 +266,7 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->counters);
   cudaFree(s->timeline);
   cudaFree(s->tile_keys); cudaFree(s->tile_arrivals);
-  for(int i = 0; i < 3; ++i) { cudaFree(s->heavy_list[i]); cudaFree(s->light_list[i]); }
+  for(int i = 0; i < 3; ++i) { cudaFree(s->heavy_list[i]); cudaFree(s->light_list[i]); cudaFree(s->sparse_list[i]); }
   cudaFree(s->work_counts);
   cudaFree(s->cursor);
   cudaFree(s->chain_state);
@@ -405,6 +406,8 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.heavy_min_items = s->tune[4]; P.split_avg_pct = s->tune[5]; P.pdl = s->tune[6];
     P.heavy_cur = s->heavy_list[f % 3]; P.heavy_next = s->heavy_list[(f + 1) % 3];
     P.light_cur = s->light_list[f % 3]; P.light_next = s->light_list[(f + 1) % 3];
+    P.sparse_cur = s->sparse_list[f % 3]; P.sparse_next = s->sparse_list[(f + 1) % 3];
+    P.warp_tile_max_seeds = s->tune[7];
     P.counts_cur = s->work_counts + 8 * (f % 3);
     P.counts_next = s->work_counts + 8 * ((f + 1) % 3);
     P.counts_zero = s->work_counts + 8 * ((f + 2) % 3);
@@ -631,6 +634,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[0] = staged::SPLIT_MAX; s->tune[1] = staged::SPLIT_MIN_ITEMS;
   s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
   s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT; s->tune[6] = 1;
+  s->tune[7] = staged::WARP_TILE_MAX_SEEDS;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
   s->chain_frames = STAGED_BATCH_MAX;
   const int rc = seeds_alloc(s);
@@ -703,7 +707,10 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   }
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
   case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT: case RMD_OPT_TUNE_PDL:
-    RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL) ? 0 : 1) && value <= 65535, "tuning value out of range");
+  case RMD_OPT_TUNE_WARP_TILE_SEEDS:
+    RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL ||
+                           option == RMD_OPT_TUNE_WARP_TILE_SEEDS) ? 0 : 1) && value <= 65535, "tuning value out of range");
+    RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= staged::WARP_TILE_MAX_SEEDS, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..8");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
     return 0;

@@ -230,6 +230,7 @@ __global__ void worklist_init_kernel(unsigned int *light, unsigned int *counts, 
   {
     counts[0] = 0u; counts[1] = (unsigned int)n_tiles; counts[2] = 0u; counts[3] = 0u;
     counts[4] = (unsigned int)n_tiles; counts[5] = 0u;   // every tile listed once; see FilterParams::counts_cur
+    counts[6] = 0u; counts[7] = 0u;
   }
 }
 

@@ -84,7 +84,7 @@ struct __align__(128) StagedSmem
   int strip_ox, strip_oy, strip_w, strip_rows;
   int is_last;
   unsigned int fetch;                  // index of the work-list entry this CTA processes next (persistent loop)
-  unsigned int fetch_heavy, fetch_light;  // chain mode: the frame's list sizes, read BEFORE the index was drawn
+  unsigned int fetch_heavy, fetch_light, fetch_sparse;  // chain mode: the frame's list sizes, read BEFORE the index was drawn
   int items_acc;                       // work items of the tile (sum of the seeds' chunk counts)
   unsigned int row_active[TILE_H];     // ballot of the seeds to update, per pixel row
   unsigned long long mbar;
@@ -203,6 +203,184 @@ __device__ __forceinline__ int to_int_clamped(float v)
 
 } // namespace
 
+
+// ------------------------------------------------------------ per-seed steps shared by the CTA and warp paths
+
+constexpr unsigned long long K_NO_MATCH = 0x407FFFFF00000000ull;   // orderable(-1.0f) << 32: "no candidate scored"
+
+// src/seed_check.cu:37-66 for one pixel; `prev` is the state the previous frame left (absorbing states are final
+// when P.trust_conv says the map agrees with the parameters).
+template<int PS>
+__device__ __forceinline__ int classify_pixel(const FilterParams &P, const int x, const int y, const int prev,
+                                              const float4 seed, bool &active)
+{
+  active = false;
+  if(P.trust_conv && (prev == RMD_BORDER || prev == RMD_CONVERGED || prev == RMD_DIVERGED))
+    return prev;
+  if((x > P.width - PS - 1) || (y > P.height - PS - 1) || (x < PS) || (y < PS))
+    return RMD_BORDER;
+  const int state = classify_seed(P, seed);
+  active = (state == RMD_UPDATE);
+  return state;
+}
+
+// The candidate positions follow the reference's own float accumulation of l (epipolar_match.cu:88).  One cheap
+// pass counts them and records l every 16th candidate in ckpt[] (work items and the final match restart from a
+// checkpoint, bit-identically).  l only grows, so a block of 16 additions needs one end test, not 16: the same
+// additions in the same order as the reference's loop, a fifth of the instructions of the naive transcription.
+__device__ __forceinline__ int count_candidates(const float half_len, float *ckpt)
+{
+  int k = 0;
+  float l = -half_len;
+  while(l <= half_len && k < L_CHECKPOINT_STEP * L_CHECKPOINTS)
+  {
+    ckpt[k / L_CHECKPOINT_STEP] = l;
+    float l_blk = l;
+#pragma unroll
+    for(int t = 0; t < L_CHECKPOINT_STEP; ++t) l_blk += RMD_EPIPOLAR_STEP;
+    if(l_blk <= half_len)
+    {
+      l = l_blk;              // candidates k .. k+16 all exist
+      k += L_CHECKPOINT_STEP;
+      continue;
+    }
+    int t = 1;                // the last candidate is k + t - 1, 1 <= t <= 16
+    for(l += RMD_EPIPOLAR_STEP; t < L_CHECKPOINT_STEP && l <= half_len; l += RMD_EPIPOLAR_STEP) ++t;
+    k += t;
+    break;
+  }
+  return k;
+}
+
+// l of candidate k: restart from the checkpoint, at most 15 of the reference's additions
+__device__ __forceinline__ float candidate_l(const float *ckpt, const int k)
+{
+  float l = ckpt[k / L_CHECKPOINT_STEP];
+  for(int t = 0; t < (k & (L_CHECKPOINT_STEP - 1)); ++t) l += RMD_EPIPOLAR_STEP;
+  return l;
+}
+
+// The candidates that pass the image-bounds test (epipolar_match.cu:91-97) form one contiguous index range
+// [k_lo, k_hi] -- the segment is a straight line, the accepted region convex and float rounding monotone -- so
+// everything outside it is skipped wholesale and seeds whose projection left the image cost no work.  The range
+// is estimated in closed form and then fixed EXACTLY by testing the real candidates around the estimate.
+// k_hi < 0: none.
+template<int PS>
+__device__ __forceinline__ void accepted_range(const FilterParams &P, const EpiSegment &seg, const int n_cand,
+                                               const float *ckpt, int &k_lo, int &k_hi)
+{
+  k_lo = INT_MAX; k_hi = -1;
+  if(n_cand <= 0)
+    return;
+  auto accepted = [&](int k) -> bool
+  {
+    const float l = candidate_l(ckpt, k);
+    const float2 px = candidate_px(seg.mean.x, seg.mean.y, seg.dir.x, seg.dir.y, l);
+    return !candidate_rejected<PS>(px, P.width, P.height);
+  };
+  // l-interval in which P <= mean + l*dir < size - P holds, per axis
+  float la = -1.0e30f, lb = 1.0e30f;
+  bool none = false, exact_scan = false;
+  {
+    const float lo_x = (float)PS, hi_x = (float)(P.width - PS), lo_y = (float)PS, hi_y = (float)(P.height - PS);
+    const float m[2] = {seg.mean.x, seg.mean.y}, d[2] = {seg.dir.x, seg.dir.y};
+    const float lo[2] = {lo_x, lo_y}, hi[2] = {hi_x, hi_y};
+#pragma unroll
+    for(int ax = 0; ax < 2; ++ax)
+    {
+      if(!(fabsf(m[ax]) < 1.0e7f) || !(fabsf(d[ax]) <= 2.0f))
+        exact_scan = true;                       // NaN / inf: no shortcut
+      else if(fabsf(d[ax]) < 1.0e-6f)
+      {
+        // the segment does not move along this axis: inside, outside, or too close to call
+        if((fabsf(m[ax] - lo[ax]) <= 0.5f) || (fabsf(m[ax] - hi[ax]) <= 0.5f))
+          exact_scan = true;
+        else if((m[ax] < lo[ax]) || (m[ax] >= hi[ax]))
+          none = true;
+      }
+      else
+      {
+        const float t0 = (lo[ax] - m[ax]) / d[ax], t1 = (hi[ax] - m[ax]) / d[ax];
+        la = fmaxf(la, fminf(t0, t1));
+        lb = fminf(lb, fmaxf(t0, t1));
+      }
+    }
+  }
+  if(exact_scan)
+  {
+    for(int k = 0; k < n_cand; ++k)
+      if(accepted(k)) { k_lo = min(k_lo, k); k_hi = k; }
+  }
+  else if(!none)
+  {
+    // estimated index range, widened by 2 candidates on both sides
+    const float fa = (la + seg.half_len) / RMD_EPIPOLAR_STEP, fb = (lb + seg.half_len) / RMD_EPIPOLAR_STEP;
+    const int a = max(0, to_int_clamped(ceilf(fa)) - 2), b = min(n_cand - 1, to_int_clamped(floorf(fb)) + 2);
+    if(a <= b)
+    {
+      int first = -1, last = -1;
+      for(int k = a; k <= min(a + 4, b); ++k)
+        if(accepted(k)) { first = k; break; }
+      for(int k = b; k >= max(b - 4, a); --k)
+        if(accepted(k)) { last = k; break; }
+      if(first >= 0 && last >= 0)
+      {
+        // the estimate must have bracketed the true ends; if an end sits on
+        // the widened border (and is not the segment's end) scan further
+        while(first > 0 && first == a && accepted(first - 1)) { --first; }
+        while(last < n_cand - 1 && last == b && accepted(last + 1)) { ++last; }
+        k_lo = first; k_hi = last;
+      }
+      else if(b - a > 4)
+      {
+        // an end was not found next to its estimate: be exact over the whole window
+        for(int k = a; k <= b; ++k)
+          if(accepted(k)) { k_lo = min(k_lo, k); k_hi = k; }
+      }
+    }
+  }
+}
+
+// Phase 4 for one seed that was searched: NO_MATCH (b += 1, seed_update.cu:113-117) or triangulation + Bayesian
+// update from the best candidate (key = (orderable(ncc) << 32) | ~index, K_NO_MATCH if nothing was scored).
+template<int PS>
+__device__ __forceinline__ void apply_match(const FilterParams &P, const int x, const int y, const EpiSegment &seg,
+                                            const int n_cand, const unsigned long long key, const float *ckpt,
+                                            float4 seed, float4 *seed_ptr, const int prev, int *conv_ptr)
+{
+  int state = RMD_UPDATE;
+  if(key == K_NO_MATCH || !(n_cand > 0))
+  {
+    state = RMD_NO_MATCH;
+  }
+  else
+  {
+    const unsigned int hi = (unsigned int)(key >> 32);
+    const float best_ncc = __uint_as_float((hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi);
+    if(best_ncc < RMD_NCC_ACCEPT)
+    {
+      state = RMD_NO_MATCH;
+    }
+    else
+    {
+      const int best_idx = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull));
+      const float l = candidate_l(ckpt, best_idx);
+      const float2 best_px = candidate_px(seg.mean.x, seg.mean.y, seg.dir.x, seg.dir.y, l);
+      if(P.matches)
+        P.matches[(size_t)y * P.match_stride + x] = best_px;
+      if(bayes_update(P, x, y, best_px, seed))
+        *seed_ptr = seed;
+    }
+  }
+  if(state == RMD_NO_MATCH)
+  {
+    seed.w += 1.0f;  // seed_update.cu:113-117
+    *seed_ptr = seed;
+  }
+  if(state != prev)
+    *conv_ptr = state;
+}
+
 // One entry of a keyframe's work list: phases 0-4 for one tile (or one share of a split tile).
 // `mbar_phase` is the parity of the CTA's TMA mbarrier, carried from tile to tile.
 template<int PS>
@@ -268,19 +446,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     // (L2 loads: in chain mode the previous frame's finaliser may have run on another SM during this launch)
     prev = __ldcg(conv_ptr);
     seed = __ldcg(seed_ptr);   // issued with the state load, not after it: one memory round trip for the tile
-    if(P.trust_conv && (prev == RMD_BORDER || prev == RMD_CONVERGED || prev == RMD_DIVERGED))
-    {
-      state = prev;
-    }
-    else if((x > P.width - PS - 1) || (y > P.height - PS - 1) || (x < PS) || (y < PS))
-    {
-      state = RMD_BORDER;
-    }
-    else
-    {
-      state = classify_seed(P, seed);
-      active = (state == RMD_UPDATE);
-    }
+    state = classify_pixel<PS>(P, x, y, prev, seed, active);
     converged = (state == RMD_CONVERGED);
     if(lead && !active && state != prev)
       *conv_ptr = state;
@@ -308,7 +474,10 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
         atomicAdd(any_pending ? P.converged_now : P.retired_converged, (unsigned int)__popc(conv_ballot));
       if(tid == 0 && any_pending)
       {
-        P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
+        if(P.warp_tile_max_seeds > 0)
+          P.sparse_next[atomicAdd(P.counts_next + 6, 1u)] = (unsigned int)tile;     // nothing to update now: cheapest class
+        else
+          P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
         atomicAdd(P.counts_next + 4, 1u);
       }
       if(chain)
@@ -337,111 +506,8 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
   {
     const float2 stats = __ldg(P.templ + (size_t)y * P.templ_stride + x);
     seg = epipolar_segment(P, x, y, seed.x, seed.y);
-    // The candidate positions follow the reference's own float accumulation of l
-    // (epipolar_match.cu:88).  One cheap pass counts them and records l every
-    // 16th candidate (work items and the final match restart from a checkpoint,
-    // bit-identically).  The candidates that pass the image-bounds test (:91-97)
-    // form one contiguous index range [k_lo, k_hi] -- the segment is a straight
-    // line, the accepted region convex and float rounding monotone -- so
-    // everything outside it is skipped wholesale and seeds whose projection left
-    // the image cost no work items.  The range is estimated in closed form and
-    // then fixed EXACTLY by testing the real candidates around the estimate.
-    // l only grows, so a block of 16 additions needs one end test, not 16:
-    // the same additions in the same order as the reference's loop, a fifth of
-    // the instructions of the naive transcription.
-    {
-      int k = 0;
-      float l = -seg.half_len;
-      while(l <= seg.half_len && k < L_CHECKPOINT_STEP * L_CHECKPOINTS)
-      {
-        S.l_checkpoint[pix][k / L_CHECKPOINT_STEP] = l;
-        float l_blk = l;
-#pragma unroll
-        for(int t = 0; t < L_CHECKPOINT_STEP; ++t) l_blk += RMD_EPIPOLAR_STEP;
-        if(l_blk <= seg.half_len)
-        {
-          l = l_blk;              // candidates k .. k+16 all exist
-          k += L_CHECKPOINT_STEP;
-          continue;
-        }
-        int t = 1;                // the last candidate is k + t - 1, 1 <= t <= 16
-        for(l += RMD_EPIPOLAR_STEP; t < L_CHECKPOINT_STEP && l <= seg.half_len; l += RMD_EPIPOLAR_STEP) ++t;
-        k += t;
-        break;
-      }
-      n_cand = k;
-    }
-    if(n_cand > 0)
-    {
-      auto accepted = [&](int k) -> bool
-      {
-        float l = S.l_checkpoint[pix][k / L_CHECKPOINT_STEP];
-        for(int t = 0; t < (k & (L_CHECKPOINT_STEP - 1)); ++t) l += RMD_EPIPOLAR_STEP;
-        const float2 px = candidate_px(seg.mean.x, seg.mean.y, seg.dir.x, seg.dir.y, l);
-        return !candidate_rejected<PS>(px, P.width, P.height);
-      };
-      // l-interval in which P <= mean + l*dir < size - P holds, per axis
-      float la = -1.0e30f, lb = 1.0e30f;
-      bool none = false, exact_scan = false;
-      {
-        const float lo_x = (float)PS, hi_x = (float)(P.width - PS), lo_y = (float)PS, hi_y = (float)(P.height - PS);
-        const float m[2] = {seg.mean.x, seg.mean.y}, d[2] = {seg.dir.x, seg.dir.y};
-        const float lo[2] = {lo_x, lo_y}, hi[2] = {hi_x, hi_y};
-#pragma unroll
-        for(int ax = 0; ax < 2; ++ax)
-        {
-          if(!(fabsf(m[ax]) < 1.0e7f) || !(fabsf(d[ax]) <= 2.0f))
-            exact_scan = true;                       // NaN / inf: no shortcut
-          else if(fabsf(d[ax]) < 1.0e-6f)
-          {
-            // the segment does not move along this axis: inside, outside, or too close to call
-            if((fabsf(m[ax] - lo[ax]) <= 0.5f) || (fabsf(m[ax] - hi[ax]) <= 0.5f))
-              exact_scan = true;
-            else if((m[ax] < lo[ax]) || (m[ax] >= hi[ax]))
-              none = true;
-          }
-          else
-          {
-            const float t0 = (lo[ax] - m[ax]) / d[ax], t1 = (hi[ax] - m[ax]) / d[ax];
-            la = fmaxf(la, fminf(t0, t1));
-            lb = fminf(lb, fmaxf(t0, t1));
-          }
-        }
-      }
-      if(exact_scan)
-      {
-        for(int k = 0; k < n_cand; ++k)
-          if(accepted(k)) { k_lo = min(k_lo, k); k_hi = k; }
-      }
-      else if(!none)
-      {
-        // estimated index range, widened by 2 candidates on both sides
-        const float fa = (la + seg.half_len) / RMD_EPIPOLAR_STEP, fb = (lb + seg.half_len) / RMD_EPIPOLAR_STEP;
-        const int a = max(0, to_int_clamped(ceilf(fa)) - 2), b = min(n_cand - 1, to_int_clamped(floorf(fb)) + 2);
-        if(a <= b)
-        {
-          int first = -1, last = -1;
-          for(int k = a; k <= min(a + 4, b); ++k)
-            if(accepted(k)) { first = k; break; }
-          for(int k = b; k >= max(b - 4, a); --k)
-            if(accepted(k)) { last = k; break; }
-          if(first >= 0 && last >= 0)
-          {
-            // the estimate must have bracketed the true ends; if an end sits on
-            // the widened border (and is not the segment's end) scan further
-            while(first > 0 && first == a && accepted(first - 1)) { --first; }
-            while(last < n_cand - 1 && last == b && accepted(last + 1)) { ++last; }
-            k_lo = first; k_hi = last;
-          }
-          else if(b - a > 4)
-          {
-            // an end was not found next to its estimate: be exact over the whole window
-            for(int k = a; k <= b; ++k)
-              if(accepted(k)) { k_lo = min(k_lo, k); k_hi = k; }
-          }
-        }
-      }
-    }
+    n_cand = count_candidates(seg.half_len, S.l_checkpoint[pix]);
+    accepted_range<PS>(P, seg, n_cand, S.l_checkpoint[pix], k_lo, k_hi);
     const float ex0 = seg.mean.x - seg.half_len * seg.dir.x, ex1 = seg.mean.x + seg.half_len * seg.dir.x;
     const float ey0 = seg.mean.y - seg.half_len * seg.dir.y, ey1 = seg.mean.y + seg.half_len * seg.dir.y;
     int xl = to_int_clamped(floorf(fminf(ex0, ex1))) - (PS / 2 + 1);
@@ -461,7 +527,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     r.n = (k_hi >= 0) ? (k_lo | (k_hi << 8) | (1 << 16)) : 0;  // accepted candidate range, packed
     S.rec[pix] = r;
   }
-  const unsigned long long kNoMatch = ((unsigned long long)orderable(-1.0f)) << 32;
+  const unsigned long long kNoMatch = K_NO_MATCH;
   S.best[pix] = kNoMatch;
   const int m_chunks = (k_hi >= 0) ? (k_hi / CHUNK - k_lo / CHUNK + 1) : 0;  // chunks with accepted candidates
   {
@@ -529,7 +595,11 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       const int reserved = (int)atomicAdd(P.counts_next + 2, (unsigned int)(znext - 1));
       znext = 1 + max(0, min(znext - 1, P.helper_cap - reserved));   // what fits in the list
     }
-    if(znext > 1 || items >= P.heavy_min_items)
+    if(znext == 1 && n_active <= P.warp_tile_max_seeds && S.centroid[2] <= WARP_TILE_MAX_CANDS)
+    {
+      P.sparse_next[atomicAdd(P.counts_next + 6, 1u)] = (unsigned int)tile;   // a handful of seeds, a few dozen candidates
+    }
+    else if(znext > 1 || items >= P.heavy_min_items)
     {
       const unsigned int base = atomicAdd(P.counts_next + 0, (unsigned int)znext);
       for(int k = 0; k < znext; ++k)
@@ -849,39 +919,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
 
   // ---- 4. triangulation + Bayesian update by the owner of the seed
   if(active)
-  {
-    if(key == kNoMatch || !(n_cand > 0))
-    {
-      state = RMD_NO_MATCH;
-    }
-    else
-    {
-      const unsigned int hi = (unsigned int)(key >> 32);
-      const float best_ncc = __uint_as_float((hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi);
-      if(best_ncc < RMD_NCC_ACCEPT)
-      {
-        state = RMD_NO_MATCH;
-      }
-      else
-      {
-        const int best_idx = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffull));
-        float l = S.l_checkpoint[pix][best_idx / L_CHECKPOINT_STEP];
-        for(int k = 0; k < (best_idx & (L_CHECKPOINT_STEP - 1)); ++k) l += RMD_EPIPOLAR_STEP;
-        const float2 best_px = candidate_px(seg.mean.x, seg.mean.y, seg.dir.x, seg.dir.y, l);
-        if(P.matches)
-          P.matches[(size_t)y * P.match_stride + x] = best_px;
-        if(bayes_update(P, x, y, best_px, seed))
-          *seed_ptr = seed;
-      }
-    }
-    if(state == RMD_NO_MATCH)
-    {
-      seed.w += 1.0f;  // seed_update.cu:113-117
-      *seed_ptr = seed;
-    }
-    if(state != prev)
-      *conv_ptr = state;
-  }
+    apply_match<PS>(P, x, y, seg, n_cand, key, S.l_checkpoint[pix], seed, seed_ptr, prev, conv_ptr);
   if(chain)
   {
     __threadfence();            // seeds and states of this frame ...
@@ -892,6 +930,214 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
   RMD_STAMP(5);
 }
 #undef RMD_STAMP
+
+// ------------------------------------------------------------------------------------------------ warp tiles
+// Late in a keyframe two thirds of the listed tiles have a handful of seeds left to update and a few dozen
+// candidates in all.  A 256-thread CTA with 64 KB of shared memory per such tile is mostly idle warps holding a
+// resident slot: here ONE WARP does the whole tile (eight tiles per CTA pass), so the slots go to the tiles that
+// need them and several keyframes' (or frames') sparse tiles pack eight to a CTA.  Same per-seed steps as the CTA
+// path (classify_pixel, epipolar_segment, count_candidates, accepted_range, ncc_score, apply_match), hence the
+// same results: lanes = the tile's (seed, candidate) pairs, taps from global memory (L2), per-seed arg-max by
+// shared-memory atomicMax on the same (ncc, ~index) key.
+struct alignas(16) WarpTileSmem
+{
+  SearchRec rec[WARP_TILE_MAX_SEEDS];
+  unsigned long long best[WARP_TILE_MAX_SEEDS];
+  float l_checkpoint[WARP_TILE_MAX_SEEDS][L_CHECKPOINTS];
+  int cum[WARP_TILE_MAX_SEEDS];    // candidates of the batch's seeds 0..i (inclusive prefix)
+  int pos[WARP_TILE_MAX_SEEDS];    // x | y << 16 of the seed
+};
+static_assert(sizeof(WarpTileSmem) * NWARPS <= STRIP_FLOATS * sizeof(float), "warp-tile scratch aliases the strip");
+
+template<int PS>
+__device__ __forceinline__ void process_warp_tile(const FilterParams &P, StagedSmem<PS> &S, const unsigned int entry,
+                                                  const bool chain, const bool wait_prev, unsigned int *error_flag)
+{
+  const int lane = threadIdx.x, wid = threadIdx.y;
+  WarpTileSmem &Wt = reinterpret_cast<WarpTileSmem*>(S.strip)[wid];
+  const int tile = (int)(entry & 0xfffffu);
+  const int x0 = (tile % P.tiles_x) * TILE_W, y0 = (tile / P.tiles_x) * TILE_H;
+  const int x = x0 + lane;
+  if(wait_prev)
+  {
+    if(lane == 0 && !wait_at_least(P.tile_done + tile, P.frame_no - 1u))
+      atomicExch(error_flag, 1u);
+    __syncwarp();
+  }
+  // ---- 0. classification of the tile's 8 rows (lane = column)
+  unsigned int act[TILE_H];
+  int n_conv = 0;
+  unsigned int pending_any = 0u;
+#pragma unroll
+  for(int r = 0; r < TILE_H; ++r)
+  {
+    const int y = y0 + r;
+    const bool inside = (x < P.width) && (y < P.height);
+    bool active = false;
+    int state = RMD_BORDER;
+    if(inside)
+    {
+      int *conv_ptr = P.conv + (size_t)y * P.conv_stride + x;
+      const int prev = __ldcg(conv_ptr);
+      const float4 seed = __ldcg(P.seed + (size_t)y * P.seed_stride + x);
+      state = classify_pixel<PS>(P, x, y, prev, seed, active);
+      if(!active && state != prev)
+        *conv_ptr = state;
+    }
+    act[r] = __ballot_sync(0xffffffffu, active);
+    n_conv += __popc(__ballot_sync(0xffffffffu, state == RMD_CONVERGED));
+    pending_any |= __ballot_sync(0xffffffffu, inside && !(state == RMD_BORDER || state == RMD_CONVERGED || state == RMD_DIVERGED));
+  }
+  int n_act = 0;
+#pragma unroll
+  for(int r = 0; r < TILE_H; ++r) n_act += __popc(act[r]);
+  if(n_act == 0)
+  {
+    if(lane == 0)
+    {
+      if(n_conv)
+        atomicAdd(pending_any ? P.converged_now : P.retired_converged, (unsigned int)n_conv);
+      if(pending_any)
+      {
+        P.sparse_next[atomicAdd(P.counts_next + 6, 1u)] = (unsigned int)tile;
+        atomicAdd(P.counts_next + 4, 1u);
+      }
+      if(chain)
+        signal_listed(P);
+    }
+    if(chain)
+    {
+      __threadfence();
+      __syncwarp();
+      if(lane == 0)
+        st_release(P.tile_done + tile, P.frame_no);
+    }
+    return;
+  }
+  if(lane == 0 && n_conv)
+    atomicAdd(P.converged_now, (unsigned int)n_conv);
+
+  // ---- seeds to update, in pixel order, WARP_TILE_MAX_SEEDS at a time (one batch unless the list was stale)
+  int items = 0, total_cands = 0;
+  for(int base = 0; base < n_act; base += WARP_TILE_MAX_SEEDS)
+  {
+    const int slot = lane - base;
+    const bool mine = (slot >= 0) && (slot < WARP_TILE_MAX_SEEDS) && (lane < n_act);
+    // my seed: the lane-th set bit of act[0..7]
+    int sx = 0, sy = 0;
+    {
+      int acc = 0, found = 0;
+#pragma unroll
+      for(int r = 0; r < TILE_H; ++r)
+      {
+        const int cnt = __popc(act[r]);
+        if(!found && lane < acc + cnt)
+        {
+          sy = y0 + r;
+          sx = x0 + (int)__fns(act[r], 0, lane - acc + 1);
+          found = 1;
+        }
+        acc += cnt;
+      }
+    }
+    // ---- 1. set-up by the seed's lane
+    EpiSegment seg;
+    seg.mean = make_float2(0.f, 0.f); seg.dir = make_float2(0.f, 0.f); seg.half_len = 0.f;
+    float4 seed = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 *seed_ptr = nullptr;
+    int *conv_ptr = nullptr;
+    int prev = RMD_UPDATE, n_cand = 0, k_lo = INT_MAX, k_hi = -1, cnt = 0;
+    if(mine)
+    {
+      seed_ptr = P.seed + (size_t)sy * P.seed_stride + sx;
+      conv_ptr = P.conv + (size_t)sy * P.conv_stride + sx;
+      seed = __ldcg(seed_ptr);
+      prev = __ldcg(conv_ptr);
+      const float2 stats = __ldg(P.templ + (size_t)sy * P.templ_stride + sx);
+      seg = epipolar_segment(P, sx, sy, seed.x, seed.y);
+      n_cand = count_candidates(seg.half_len, Wt.l_checkpoint[slot]);
+      accepted_range<PS>(P, seg, n_cand, Wt.l_checkpoint[slot], k_lo, k_hi);
+      cnt = (k_hi >= 0) ? (k_hi - k_lo + 1) : 0;
+      SearchRec rec;
+      rec.mean_x = seg.mean.x; rec.mean_y = seg.mean.y; rec.dir_x = seg.dir.x; rec.dir_y = seg.dir.y;
+      rec.half_len = seg.half_len; rec.sum_templ = stats.x; rec.denom = stats.y;
+      rec.n = (k_hi >= 0) ? k_lo : 0;
+      Wt.rec[slot] = rec;
+      Wt.best[slot] = K_NO_MATCH;
+      Wt.pos[slot] = sx | (sy << 16);
+      items += (k_hi >= 0) ? (k_hi / CHUNK - k_lo / CHUNK + 1) : 0;
+    }
+    // inclusive prefix of the batch's candidate counts (lanes base .. base+7)
+    {
+      int inc = mine ? cnt : 0;
+#pragma unroll
+      for(int off = 1; off < WARP_TILE_MAX_SEEDS; off <<= 1)
+      {
+        const int up = __shfl_up_sync(0xffffffffu, inc, off);
+        if(slot >= off) inc += up;
+      }
+      if(slot >= 0 && slot < WARP_TILE_MAX_SEEDS)
+        Wt.cum[slot] = inc;     // lanes past n_act carry the running total: cum[] is non-decreasing over all 8 slots
+    }
+    __syncwarp();
+    const int batch_cands = Wt.cum[WARP_TILE_MAX_SEEDS - 1];
+    total_cands += batch_cands;
+    // ---- 3. NCC search: lane = (seed, candidate) pair of the batch
+#pragma unroll 1
+    for(int q = lane; q < batch_cands; q += 32)
+    {
+      int j = 0;
+#pragma unroll
+      for(int i = 0; i < WARP_TILE_MAX_SEEDS - 1; ++i) j += (Wt.cum[i] <= q) ? 1 : 0;
+      const SearchRec R = Wt.rec[j];
+      const int k = R.n + q - (j ? Wt.cum[j - 1] : 0);
+      const int px0 = Wt.pos[j] & 0xffff, py0 = Wt.pos[j] >> 16;
+      const float l = candidate_l(Wt.l_checkpoint[j], k);
+      const float2 px = candidate_px(R.mean_x, R.mean_y, R.dir_x, R.dir_y, l);
+      if(candidate_rejected<PS>(px, P.width, P.height))
+        continue;
+      float templ[PS * PS];
+#pragma unroll
+      for(int jj = 0; jj < PS; ++jj)
+#pragma unroll
+        for(int ii = 0; ii < PS; ++ii)
+          templ[jj * PS + ii] = __ldg(P.ref + (size_t)(py0 - PS / 2 + jj) * P.ref_stride + (px0 - PS / 2 + ii));
+      const TapFrame frame = tap_frame<PS>(px, P.tex_quant);
+      const GlobalTaps taps(P.curr, P.curr_stride, frame);
+      const float ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+      if(ncc > -1.0f)
+        atomicMax(&Wt.best[j], (((unsigned long long)orderable(ncc)) << 32) |
+                                   (unsigned long long)(0xffffffffu - (unsigned int)k));
+    }
+    __syncwarp();
+    // ---- 4. update by the seed's lane
+    if(mine)
+      apply_match<PS>(P, sx, sy, seg, n_cand, Wt.best[slot], Wt.l_checkpoint[slot], seed, seed_ptr, prev, conv_ptr);
+    __syncwarp();
+  }
+  items = __reduce_add_sync(0xffffffffu, items);
+  // ---- this tile's entry in the NEXT frame's work list
+  if(lane == 0)
+  {
+    atomicAdd(P.counts_next + 3, (unsigned int)items);
+    if(n_act <= P.warp_tile_max_seeds && total_cands <= WARP_TILE_MAX_CANDS)
+      P.sparse_next[atomicAdd(P.counts_next + 6, 1u)] = (unsigned int)tile;
+    else if(items >= P.heavy_min_items)
+      P.heavy_next[atomicAdd(P.counts_next + 0, 1u)] = (unsigned int)tile | (1u << 26);
+    else
+      P.light_next[atomicAdd(P.counts_next + 1, 1u)] = (unsigned int)tile | (1u << 26);
+    atomicAdd(P.counts_next + 4, 1u);
+    if(chain)
+      signal_listed(P);
+  }
+  if(chain)
+  {
+    __threadfence();
+    __syncwarp();
+    if(lane == 0)
+      st_release(P.tile_done + tile, P.frame_no);
+  }
+}
 
 // The launch: a persistent grid (one CTA per resident slot).  Every CTA pulls entries of the frame's work
 // list(s) through one cursor until they run out, so a frame costs one wave however many tiles it lists:
@@ -925,7 +1171,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
       const FilterParams &P = B.p[K == 1 ? 0 : k];
       *P.converged_next = 0u;
 #pragma unroll
-      for(int w = 0; w < 6; ++w) P.counts_zero[w] = 0u;
+      for(int w = 0; w < 8; ++w) P.counts_zero[w] = 0u;
     }
   }
   if(tid == 0)
@@ -948,6 +1194,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
         // that finds this frame's cursor exhausted, i.e. after every valid index has been drawn.
         S.fetch_heavy = __ldcg(P.counts_cur + 0);
         S.fetch_light = __ldcg(P.counts_cur + 1);
+        S.fetch_sparse = __ldcg(P.counts_cur + 6);
         __threadfence();
       }
       S.fetch = atomicAdd(B.cursor + (chain ? g : 0), 1u);
@@ -956,12 +1203,16 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
     const unsigned int i = S.fetch;
     int kf = -1;
     unsigned int entry = 0u;
+    int sparse_group = -1;           // >= 0: the index is a group of 8 warp tiles (one per warp) of keyframe / frame kf
+    unsigned int n_sparse = 0u;
     if(chain)
     {
       const FilterParams &P = B.p[K == 1 ? 0 : g];
       const unsigned int n_heavy = S.fetch_heavy, n_light = S.fetch_light;
+      n_sparse = S.fetch_sparse;
       if(i < n_heavy) { kf = g; entry = __ldcg(P.heavy_cur + i); }
       else if(i - n_heavy < n_light) { kf = g; entry = __ldcg(P.light_cur + (i - n_heavy)); }
+      else if(i - n_heavy - n_light < (n_sparse + NWARPS - 1) / NWARPS) { kf = g; sparse_group = (int)(i - n_heavy - n_light); }
       if(i == 0u && tid == 0)
       {
         // whoever starts a frame clears what the NEXT frame will accumulate into (nobody uses those slots
@@ -969,7 +1220,7 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
         // this frame's list was complete)
         *P.converged_next = 0u;
 #pragma unroll
-        for(int w = 0; w < 6; ++w) P.counts_zero[w] = 0u;
+        for(int w = 0; w < 8; ++w) P.counts_zero[w] = 0u;
         if(__ldcg(P.counts_cur + 4) == 0u)
         {
           // nothing listed (every tile has retired): no lead CTA will publish the next frame's (empty) list
@@ -1006,10 +1257,26 @@ __global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_stag
         if(i - base < n_light) { kf = k; entry = P.light_cur[i - base]; }
         base += n_light;
       }
+#pragma unroll 1
+      for(int k = 0; k < n_kf && kf < 0; ++k)
+      {
+        const FilterParams &P = B.p[K == 1 ? 0 : k];
+        const unsigned int ns = P.counts_cur[6], groups = (ns + NWARPS - 1) / NWARPS;
+        if(i - base < groups) { kf = k; sparse_group = (int)(i - base); n_sparse = ns; }
+        base += groups;
+      }
       if(kf < 0)
         break;           // the lists are exhausted (uniform: every thread read the same index)
     }
-    process_tile<PS>(B.p[K == 1 ? 0 : kf], B.m[K == 1 ? 0 : kf], S, entry, mbar_phase, chain, chain && g > 0, error_flag);
+    if(sparse_group >= 0)
+    {
+      const FilterParams &P = B.p[K == 1 ? 0 : kf];
+      const unsigned int e = (unsigned int)sparse_group * NWARPS + threadIdx.y;
+      if(e < n_sparse)
+        process_warp_tile<PS>(P, S, __ldcg(P.sparse_cur + e), chain, chain && g > 0, error_flag);
+    }
+    else
+      process_tile<PS>(B.p[K == 1 ? 0 : kf], B.m[K == 1 ? 0 : kf], S, entry, mbar_phase, chain, chain && g > 0, error_flag);
     __syncthreads();   // S.fetch and the tile's shared state are free again
   }
   // the last CTA out rewinds the cursor for the next launch (launches on a stream are ordered)

@@ -118,8 +118,13 @@ struct FilterParams
   // are counted once in *retired_converged).
   const unsigned int *heavy_cur, *light_cur;
   unsigned int *heavy_next, *light_next;
+  // Third class: tiles with a handful of seeds left to update and a few dozen candidates in all.  They are
+  // processed by ONE WARP each (eight per CTA), entry = tile; counts[6] entries.
+  const unsigned int *sparse_cur;
+  unsigned int *sparse_next;
+  int warp_tile_max_seeds;               // 0: no warp tiles
   // {heavy entries, light entries, helper entries reserved, work items of the frame, tiles listed (lead
-  //  entries), lead CTAs of the previous frame that have finished listing, -, -}: 8 uints per frame
+  //  entries), lead CTAs of the previous frame that have finished listing, sparse entries, -}: 8 uints per frame
   const unsigned int *counts_cur;
   unsigned int *counts_next, *counts_zero;
   unsigned int *retired_converged;

@@ -26,6 +26,8 @@ constexpr int SPLIT_ITEMS_PER_CTA = 384; // a helper CTA must be worth its fixed
 constexpr int HEAVY_MIN_ITEMS = 32;      // tiles with at least this many items go to the front of the work list
 constexpr int SPLIT_AVG_PCT = 100;       // ... or this percentage of the frame's items per resident-CTA slot, if larger
 constexpr int SPARSE_MAX_SEEDS = 16;     // tiles with at most this many seeds to update skip staging
+constexpr int WARP_TILE_MAX_SEEDS = 8;   // ... and with at most this many (and WARP_TILE_MAX_CANDS candidates) are done by one warp
+constexpr int WARP_TILE_MAX_CANDS = 64;
 constexpr int L_CHECKPOINT_STEP = 16;   // l is stored every 16th candidate (power of two)
 constexpr int L_CHECKPOINTS = 9;        // ceil(143 / 16)
 constexpr int STRIP_BOX_ROWS = 8;      // rows per TMA box of the strip

@@ -39,6 +39,7 @@ for stage in "$@"; do
                 timeout 300 python tools/batch_debug.py diff 3 >> $OUT/batch_debug.txt 2>&1
                 RMD_FORCE_BATCH_KERNEL=1 timeout 600 python -m pytest tests/test_gpu_worklist.py -m gpu -q -x >> $OUT/batch_debug.txt 2>&1
                 tail -n 40 $OUT/batch_debug.txt ;;
+    chain)      timeout 600 python -m pytest tests/test_full_length_parity.py -m gpu -q -x -k device_resident > $OUT/pytest_chain.log 2>&1; tail -n 15 $OUT/pytest_chain.log ;;
     batch_debug2) timeout 300 python tools/batch_debug2.py > $OUT/batch_debug2.txt 2>&1; cat $OUT/batch_debug2.txt ;;
     sanitize)   timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/batch_debug.py diff 3 > $OUT/sanitize_memcheck.txt 2>&1; tail -n 15 $OUT/sanitize_memcheck.txt
                 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/batch_debug.py same 2 > $OUT/sanitize_racecheck.txt 2>&1; tail -n 15 $OUT/sanitize_racecheck.txt ;;
