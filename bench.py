@@ -79,6 +79,8 @@ def parse_args():
     ap.add_argument("--patch", type=int, default=None)
     ap.add_argument("--denoise-iters", type=int, default=None)
     ap.add_argument("--variant", default=None, choices=[None, "staged", "direct"])
+    ap.add_argument("--chain-frames", type=int, default=None,
+                    help="frames per chained launch of the device-resident path (RMD_OPT_CHAIN_FRAMES, 1..8; default: the library's)")
     ap.add_argument("--cpu-frames", type=int, default=30,
                     help="bounded sample of the sequence for the CPU baseline (frames 1..n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -309,6 +311,8 @@ def run_ours(args, rank, world, local_rank):
     # e2e: frames live in page-locked host memory and are DMA'd in place (the contract's "host->device copy of
     # that step's inputs from pinned host memory"); pageable callers still get the staged, reusable-on-return path
     seeds.setOption(rmd.OPT_PINNED_INPUT, 1)
+    if args.chain_frames:
+        seeds.setOption(rmd.OPT_CHAIN_FRAMES, args.chain_frames)
     # A dedicated (non-default) torch stream is made current and handed to the handles, so the fused
     # kernels, the denoiser, torch's NCCL calls and the CUDA events that time them are all on one stream.
     stream = torch.cuda.Stream(dev)
@@ -465,6 +469,7 @@ def run_ours(args, rank, world, local_rank):
                    "name": args.config,
                    "parallelism": f"{world} independent keyframes, NCCL gather of final depth+convergence",
                    "kernel_variant": variant,
+                   "frames_per_launch_resident": args.chain_frames or 8,
                    "l2": "inputs larger than L2: %d distinct frames = %.0f MB streamed per step; seed state "
                          "(%.1f MB) is L2-resident by design" % (NF, NF * frame_bytes / 1e6, 28 * W * H / 1e6),
                    "final_state_hist[update,converged,border,diverged,no_match,not_visible]": conv_hist},

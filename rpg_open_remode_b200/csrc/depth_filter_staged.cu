@@ -484,10 +484,14 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       {
         if(tid == 0)
           signal_listed(P);
-        __threadfence();        // the state changes written above (conv of newly absorbing seeds) ...
+        // the state changes written above (conv of newly absorbing seeds) are visible before the tile is
+        // released: CTA barrier, then ONE cumulative gpu-scope fence + release by the signalling thread
         __syncthreads();
         if(tid == 0)
-          st_release(P.tile_done + tile, P.frame_no);   // ... are visible before the tile is released
+        {
+          __threadfence();
+          st_release(P.tile_done + tile, P.frame_no);
+        }
       }
     }
     if(stamps && tid == 0) stamps[1] = -(clock64() - stamp_t0);
@@ -922,10 +926,14 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     apply_match<PS>(P, x, y, seg, n_cand, key, S.l_checkpoint[pix], seed, seed_ptr, prev, conv_ptr);
   if(chain)
   {
-    __threadfence();            // seeds and states of this frame ...
+    // seeds and states of this frame are visible before the next frame may read them (barrier, then one
+    // cumulative gpu-scope fence + release: a fence per thread would invalidate L1 256 times per tile)
     __syncthreads();
     if(tid == 0)
-      st_release(P.tile_done + tile, P.frame_no);   // ... are visible before the next frame may read them
+    {
+      __threadfence();
+      st_release(P.tile_done + tile, P.frame_no);
+    }
   }
   RMD_STAMP(5);
 }
@@ -1007,10 +1015,12 @@ __device__ __forceinline__ void process_warp_tile(const FilterParams &P, StagedS
     }
     if(chain)
     {
-      __threadfence();
       __syncwarp();
       if(lane == 0)
+      {
+        __threadfence();
         st_release(P.tile_done + tile, P.frame_no);
+      }
     }
     return;
   }
@@ -1132,10 +1142,12 @@ __device__ __forceinline__ void process_warp_tile(const FilterParams &P, StagedS
   }
   if(chain)
   {
-    __threadfence();
     __syncwarp();
     if(lane == 0)
+    {
+      __threadfence();
       st_release(P.tile_done + tile, P.frame_no);
+    }
   }
 }
 

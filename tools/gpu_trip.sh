@@ -18,6 +18,9 @@ for stage in "$@"; do
     bench)      timeout 900 python bench.py > $OUT/bench_c2.json 2> $OUT/bench_c2.err; tail -c 600 $OUT/bench_c2.json ;;
     bench_c3)   timeout 900 python bench.py --config c3 > $OUT/bench_c3.json 2> $OUT/bench_c3.err ;;
     bench_c4)   timeout 900 python bench.py --config c4 > $OUT/bench_c4.json 2> $OUT/bench_c4.err ;;
+    bench_c4_ab) timeout 900 python bench.py --config c4 --frames 120 --no-e2e --no-cpu-baseline --chain-frames 1 > $OUT/bench_c4_chain1.json 2> $OUT/bench_c4_chain1.err
+                timeout 900 python bench.py --config c4 --frames 120 --no-e2e --no-cpu-baseline --chain-frames 8 > $OUT/bench_c4_chain8.json 2> $OUT/bench_c4_chain8.err
+                python -c "import json; [print(n, json.loads(open('gpurun_out/bench_c4_chain%d.json' % n).read())['ms_per_step']) for n in (1, 8)]" ;;
     bench_ref)  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_c2.json 2> $OUT/bench_ref_c2.err ;;
     bench_ref_c3) timeout 900 python bench.py --impl reference --config c3 --steps 2 --warmup 1 > $OUT/bench_ref_c3.json 2> $OUT/bench_ref_c3.err ;;
     bench_ref_c4) timeout 900 python bench.py --impl reference --config c4 --steps 1 --warmup 1 > $OUT/bench_ref_c4.json 2> $OUT/bench_ref_c4.err ;;

@@ -12,8 +12,10 @@ seq = synth.SyntheticSequence(W, H, seed=0x5EED0002)
 fr = [seq.frame(k, want_depth=(k == 0)) for k in range(N)]
 dmin, dmax = float(fr[0].depth.min()), float(fr[0].depth.max())
 cam = rmd.PinholeCamera(*seq.camera)
-for K in (1, 2, 4, 8):
+for K, warp_tiles in ((1, 8), (2, 8), (4, 8), (8, 8), (8, 0)):
     ks = node.KeyframeSet(W, H, cam, n=K)
+    for sd in ks.seeds:
+        sd.setOption(rmd.OPT_TUNE_WARP_TILE_SEEDS, warp_tiles)
     best = 1e9
     for rep in range(2):
         for i in range(K):
@@ -26,5 +28,5 @@ for K in (1, 2, 4, 8):
         for s in ks.seeds:
             s.sync()
         best = min(best, time.perf_counter() - t0)
-    print(f"K = {K}: {best * 1e3:7.2f} ms for {N - 1} frames -> {(N - 1) / best:8.0f} frames/s, "
+    print(f"K = {K} (warp tiles {warp_tiles}): {best * 1e3:7.2f} ms for {N - 1} frames -> {(N - 1) / best:8.0f} frames/s, "
           f"{K * (N - 1) / best:8.0f} keyframe-updates/s ({best * 1e3 / K:.2f} ms per keyframe)", flush=True)
