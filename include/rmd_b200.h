@@ -105,6 +105,10 @@ enum rmd_seeds_option {
    * are chained inside ONE persistent launch -- a tile moves on to frame k+1 as soon as its own frame k is
    * final, so frames overlap on the GPU.  Same results as one launch per frame (1). */
   RMD_OPT_CHAIN_FRAMES = 5,
+  /* Seed-major mode: once at most this percentage of the pixels is still being updated (default 8; 0 = never)
+   * the handle keeps the live seeds as a compact list and a launch walks every listed seed through its frames
+   * warp by warp -- no tiles, no per-frame synchronisation (csrc/depth_filter_seeds.cu).  Same results. */
+  RMD_OPT_SEED_MODE_PCT = 6,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */
   RMD_OPT_TUNE_SPLIT_MAX = 10,            /* most CTAs sharing one busy tile (1 = never split; default 16) */

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "librmd_b200.so")
 
-CUDA_SOURCES = ["c_api.cu", "depth_filter.cu", "depth_filter_staged.cu", "denoiser.cu", "reduction.cu", "ingest.cu", "point_cloud.cu",
+CUDA_SOURCES = ["c_api.cu", "depth_filter.cu", "depth_filter_staged.cu", "depth_filter_seeds.cu", "denoiser.cu", "reduction.cu", "ingest.cu", "point_cloud.cu",
                 "multi_gpu.cu"]
 
 NVCC_FLAGS = [

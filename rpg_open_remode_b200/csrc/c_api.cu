@@ -170,6 +170,14 @@ struct rmd_seeds
   unsigned int *chain_state;   // [n_tiles] tile_done + [1] list_ready (frame chaining, depth_filter_staged.cu)
   StagedMaps *chain_maps;      // STAGED_BATCH_MAX descriptor sets of a chained launch (allocated on first use)
   int chain_frames;            // frames per chained launch of rmd_seeds_update_device_batch (1 = one launch per frame)
+  // seed-major mode (depth_filter_seeds.cu): entered once few seeds are still updated
+  int mode;                    // 0: tile-organised kernel, 1: seed-major kernel
+  unsigned int *seed_list[2];  // compact lists of the live seeds (ping-pong between launches)
+  unsigned int *seed_ctl;      // 8 uints, see SeedModeBatch
+  int seed_cur, seed_est;      // list in use; host-side upper bound of its length
+  int seed_mode_pct;           // go seed-major when at most this percentage of the pixels is still updated (0 = never)
+  unsigned int *host_stats;    // pinned: the last frame's work-list counters, copied back asynchronously
+  cudaEvent_t stats_ev; bool stats_pending;
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
@@ -238,6 +246,12 @@ int seeds_alloc(rmd_seeds *s)
     RMD_CUDA_TRY(cudaMalloc(&s->work_counts, 24 * sizeof(unsigned int)));
     RMD_CUDA_TRY(cudaMalloc(&s->cursor, STAGED_CURSOR_WORDS * sizeof(unsigned int)));
     RMD_CUDA_TRY(cudaMemset(s->cursor, 0, STAGED_CURSOR_WORDS * sizeof(unsigned int)));
+    for(int i = 0; i < 2; ++i)
+      RMD_CUDA_TRY(cudaMalloc(&s->seed_list[i], sizeof(unsigned int) * (size_t)w * h));
+    RMD_CUDA_TRY(cudaMalloc(&s->seed_ctl, 8 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaMemset(s->seed_ctl, 0, 8 * sizeof(unsigned int)));
+    RMD_CUDA_TRY(cudaHostAlloc(&s->host_stats, 8 * sizeof(unsigned int), cudaHostAllocDefault));
+    RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->stats_ev, cudaEventDisableTiming));
     RMD_CUDA_TRY(cudaMalloc(&s->chain_state, sizeof(unsigned int) * (size_t)(s->n_tiles + 1)));
     RMD_CUDA_TRY(cudaMemset(s->chain_state, 0, sizeof(unsigned int) * (size_t)(s->n_tiles + 1)));
   }
@@ -271,6 +285,9 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->cursor);
   cudaFree(s->chain_state);
   delete[] s->chain_maps;
+  cudaFree(s->seed_list[0]); cudaFree(s->seed_list[1]); cudaFree(s->seed_ctl);
+  if(s->host_stats) cudaFreeHost(s->host_stats);
+  if(s->stats_ev) cudaEventDestroy(s->stats_ev);
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
@@ -350,6 +367,8 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   s->n_total += 1;
   s->n_total += 1;
   s->has_reference = true;
+  s->mode = 0;            // a new keyframe starts tile-organised; pending statistics belong to the old one
+  s->stats_pending = false;
   s->frame_index = 0;
   s->trust_conv = true;
   s->dist_from_ref = 0.0f;
@@ -416,7 +435,7 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.tile_done = s->chain_state;
     P.list_ready = s->chain_state + s->n_tiles;
   }
-  if(s->variant == 0)
+  if(s->variant == 0 && s->mode == 0)
   {
     if(!s->maps) s->maps = new StagedMaps();
     {
@@ -450,9 +469,97 @@ void finish_update(rmd_seeds *s)
   s->trust_conv = true;
 }
 
+// Seed-major mode is only for the staged variant without per-tile debugging / per-launch timing.
+bool seed_mode_allowed(const rmd_seeds *s)
+{
+  return s->variant == 0 && s->seed_mode_pct > 0 && !s->timeline && !s->timing;
+}
+
+// Tile mode, before a frame: has the share of seeds that are still updated (counted by the kernel two or
+// three frames ago and copied back asynchronously -- no stall) dropped below the threshold?  Then build the
+// compact list of live seeds from the convergence map and continue seed-major (depth_filter_seeds.cu).
+int maybe_enter_seed_mode(rmd_seeds *s)
+{
+  if(s->mode != 0 || !seed_mode_allowed(s) || !s->stats_pending)
+    return 0;
+  if(cudaEventQuery(s->stats_ev) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  s->stats_pending = false;
+  const unsigned int active = s->host_stats[7];
+  const size_t pixels = (size_t)s->width * s->height;
+  if((size_t)active * 100 > pixels * (size_t)s->seed_mode_pct)
+    return 0;
+  RMD_CUDA_TRY(cudaMemsetAsync(s->seed_ctl, 0, 8 * sizeof(unsigned int), s->stream));
+  RMD_CUDA_TRY(launch_seed_list_build(s->conv, (int)(s->conv_pitch / sizeof(int)), s->width, s->height,
+                                      s->seed_list[0], s->seed_ctl, s->stream));
+  s->n_total += 1;
+  s->seed_cur = 0;
+  s->seed_est = (int)active;    // the live set only shrinks: an upper bound from now on
+  s->mode = 1;
+  s->worklist_valid = false;    // the tile work list is not maintained while seed-major
+  return 0;
+}
+
+// Leave seed-major mode (state upload, variant / debugging options): the tile work list is rebuilt.
+void leave_seed_mode(rmd_seeds *s)
+{
+  if(s->mode == 1)
+  {
+    s->mode = 0;
+    s->worklist_valid = false;
+  }
+  s->stats_pending = false;
+}
+
+// Tile mode, after a frame's launch: ask for its statistics (asynchronously; one request in flight).
+int request_stats(rmd_seeds *s, const FilterParams &P)
+{
+  if(s->mode != 0 || !seed_mode_allowed(s) || s->stats_pending)
+    return 0;
+  RMD_CUDA_TRY(cudaMemcpyAsync(s->host_stats, P.counts_next, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
+  RMD_CUDA_TRY(cudaEventRecord(s->stats_ev, s->stream));
+  s->stats_pending = true;
+  return 0;
+}
+
+// One seed-major launch over n consecutive frames (device-resident: frames[k] / poses 12 * k).
+int enqueue_seed_mode(rmd_seeds *s, const float *const *frames, size_t pitch, const float *T_curr_world, int n)
+{
+  SeedModeBatch B;
+  memset(&B, 0, sizeof(B));
+  for(int k = 0; k < n; ++k)
+  {
+    const int rc = prepare_update(s, frames[k], pitch, T_curr_world + 12 * k, B.p[k]);
+    if(rc) return rc;
+  }
+  B.list_cur = s->seed_list[s->seed_cur];
+  B.list_next = s->seed_list[s->seed_cur ^ 1];
+  B.ctl = s->seed_ctl;
+  B.cur = s->seed_cur;
+  B.n_frames = n;
+  RMD_CUDA_TRY(launch_depth_filter_seeds(B, s->seed_est, s->patch, s->stream));
+  s->seed_cur ^= 1;
+  for(int k = 0; k < n; ++k)
+    finish_update(s);
+  s->n_fused -= (uint64_t)(n - 1);
+  s->n_total -= (uint64_t)(n - 1);
+  return 0;
+}
+
 // Enqueue the fused depth-filter kernel for the frame at (curr, pitch).
 int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const float *T_curr_world)
 {
+  if(s->mode == 1 && !seed_mode_allowed(s))
+    leave_seed_mode(s);
+  {
+    const int rc = maybe_enter_seed_mode(s);
+    if(rc) return rc;
+  }
+  if(s->mode == 1)
+    return enqueue_seed_mode(s, &curr, curr_pitch, T_curr_world, 1);
   FilterParams P;
   const int rc = prepare_update(s, curr, curr_pitch, T_curr_world, P);
   if(rc) return rc;
@@ -474,7 +581,7 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     s->t_valid = true;
   }
   finish_update(s);
-  return 0;
+  return request_stats(s, P);
 }
 
 // rmd::Depthmap::inputImage (src/depthmap.cpp:95-106) for a frame already on the
@@ -637,6 +744,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[7] = staged::WARP_TILE_MAX_SEEDS;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
   s->chain_frames = STAGED_BATCH_MAX;
+  s->seed_mode_pct = 8;
   const int rc = seeds_alloc(s);
   if(rc)
   {
@@ -686,7 +794,15 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     return 0;
   case RMD_OPT_KERNEL_VARIANT:
     RMD_REQUIRE(value == 0 || value == 1, "RMD_OPT_KERNEL_VARIANT: 0 (staged) or 1 (direct)");
+    if(value != s->variant)
+      leave_seed_mode(s);
     s->variant = value;
+    return 0;
+  case RMD_OPT_SEED_MODE_PCT:
+    RMD_REQUIRE(value >= 0 && value <= 100, "RMD_OPT_SEED_MODE_PCT: 0..100");
+    s->seed_mode_pct = value;
+    if(value == 0)
+      leave_seed_mode(s);
     return 0;
   case RMD_OPT_DEBUG_TIMELINE:
   {
@@ -831,7 +947,13 @@ int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t
   for(int i = 0; i < n; ++i)
   {
     const rmd_seeds *h = handles[i];
-    if(h0->variant == 0 && h->variant == 0 && h->patch == h0->patch) batch_ids[n_batch++] = i;
+    rmd_seeds *hm = handles[i];
+    if(hm->mode == 1 && !seed_mode_allowed(hm)) leave_seed_mode(hm);
+    {
+      const int rcm = maybe_enter_seed_mode(hm);
+      if(rcm) return rcm;
+    }
+    if(h0->variant == 0 && h->variant == 0 && h->patch == h0->patch && h->mode == 0 && h0->mode == 0) batch_ids[n_batch++] = i;
     else single_ids[n_single++] = i;
   }
   for(int g = 0; g < n_batch; g += STAGED_BATCH_MAX)
@@ -859,7 +981,18 @@ int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t
       RMD_CUDA_TRY(launch_depth_filter_staged(pp, mm, m, 0, h0->cursor, h0->patch, h0->stream));
     }
     for(int k = 0; k < m; ++k)
-      finish_update(handles[batch_ids[g + k]]);
+    {
+      rmd_seeds *h = handles[batch_ids[g + k]];
+      finish_update(h);
+      if(!h->stats_pending && seed_mode_allowed(h))
+      {
+        // statistics of this frame, on the stream the batch ran on
+        RMD_CUDA_TRY(cudaMemcpyAsync(h->host_stats, P[k].counts_next, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                                     h0->stream));
+        RMD_CUDA_TRY(cudaEventRecord(h->stats_ev, h0->stream));
+        h->stats_pending = true;
+      }
+    }
   }
   for(int j = 0; j < n_single; ++j)
   {
@@ -1074,6 +1207,24 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
   const int per_launch = (s->variant == 0 && !s->timeline && !s->timing) ? s->chain_frames : 1;
   for(int i = 0; i < n_frames; )
   {
+    if(s->mode == 1 && !seed_mode_allowed(s))
+      leave_seed_mode(s);
+    {
+      const int rc = maybe_enter_seed_mode(s);
+      if(rc) return rc;
+    }
+    if(s->mode == 1)
+    {
+      // seed-major: every listed seed walks through up to SEED_FRAMES_MAX frames inside one launch
+      const int m = (n_frames - i < SEED_FRAMES_MAX) ? n_frames - i : SEED_FRAMES_MAX;
+      const float *frames[SEED_FRAMES_MAX];
+      for(int k = 0; k < m; ++k)
+        frames[k] = reinterpret_cast<const float*>(base + (size_t)(i + k) * frame_stride_bytes);
+      const int rc = enqueue_seed_mode(s, frames, pitch_bytes, T_curr_world + 12 * i, m);
+      if(rc) return rc;
+      i += m;
+      continue;
+    }
     const int m = (n_frames - i < per_launch) ? n_frames - i : per_launch;
     if(m <= 1)
     {
@@ -1100,6 +1251,10 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
       finish_update(s);
     s->n_fused -= (uint64_t)(m - 1);   // launch counters count launches, not frames
     s->n_total -= (uint64_t)(m - 1);
+    {
+      const int rc = request_stats(s, P[m - 1]);
+      if(rc) return rc;
+    }
     i += m;
   }
   return 0;
@@ -1196,6 +1351,7 @@ int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   s->trust_conv = false;  // the map may no longer agree with the parameters
   s->worklist_valid = false;
+  leave_seed_mode(s);
   return 0;
 }
 
@@ -1265,6 +1421,14 @@ int rmd_seeds_converged_count(rmd_seeds_t *s, size_t *count)
 {
   RMD_REQUIRE(s && count, "rmd_seeds_converged_count: null argument");
   DeviceGuard guard(s->device);
+  if(s->mode == 1)
+  {
+    unsigned int total = 0u;
+    RMD_CUDA_TRY(cudaMemcpyAsync(&total, s->seed_ctl + 3, sizeof(total), cudaMemcpyDeviceToHost, s->stream));
+    RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *count = (size_t)total;
+    return 0;
+  }
   unsigned int v[4] = {0u, 0u, 0u, 0u};
   if(s->frame_index > 0)
   {

@@ -40,6 +40,25 @@ cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const Stage
 // Resident CTAs of the staged kernel on the current device (SMs x occupancy), 0 on error.
 int staged_cta_slots(int patch_side);
 
+// Seed-major variant for the steady state of a keyframe (depth_filter_seeds.cu): the seeds that are still
+// updated are kept as a compact list; one launch walks every listed seed through up to SEED_FRAMES_MAX
+// consecutive frames (p[f] = parameters of frame f; the work-list members of FilterParams are unused).
+// ctl: {listed seeds (ping), listed seeds (pong), group cursor, CONVERGED seeds of the keyframe, CTAs done}.
+constexpr int SEED_FRAMES_MAX = 16;
+struct alignas(16) SeedModeBatch
+{
+  FilterParams p[SEED_FRAMES_MAX];
+  const unsigned int *list_cur;    // x | y << 16 of the listed seeds, ctl[cur] of them
+  unsigned int *list_next;         // survivors are appended here, ctl[cur ^ 1] counts them (zero at launch)
+  unsigned int *ctl;
+  int cur;
+  int n_frames;
+};
+cudaError_t launch_seed_list_build(const int *conv, int conv_stride, int width, int height, unsigned int *list,
+                                   unsigned int *ctl, cudaStream_t stream);
+// max_listed: an upper bound of ctl[cur] known to the host (sizes the persistent grid only)
+cudaError_t launch_depth_filter_seeds(const SeedModeBatch &B, int max_listed, int patch_side, cudaStream_t stream);
+
 // dst[i] = value for i < n (64-bit pattern fill)
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);
 

@@ -7,7 +7,9 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 OUT=gpurun_out
-BENCH_NCU="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+# captures look at ONE frame per launch (--chain-frames 1): the 4th update = search-heavy, the 130th = steady;
+# stage ncu_chain captures a chained launch (8 frames) of the timed path as well
+BENCH_NCU="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --chain-frames 1"
 for stage in "$@"; do
   echo "=== stage $stage $(date +%T)"
   case "$stage" in
@@ -31,6 +33,7 @@ for stage in "$@"; do
                 timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 129 -c 1 -f -o $OUT/prof_staged_p5_steady $BENCH_NCU > $OUT/ncu_p5_steady.log 2>&1 ;;
     ncu_p7)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 3 -c 1 -f -o $OUT/prof_staged_p7_heavy $BENCH_NCU --config c4 --frames 140 > $OUT/ncu_p7_heavy.log 2>&1
                 timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 129 -c 1 -f -o $OUT/prof_staged_p7_steady $BENCH_NCU --config c4 --frames 140 > $OUT/ncu_p7_steady.log 2>&1 ;;
+    ncu_chain)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:depth_filter_staged -s 16 -c 1 -f -o $OUT/prof_staged_p5_chain python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_p5_chain.log 2>&1 ;;
     ncu_denoise) timeout 900 ncu --set full --clock-control none --import-source on -k regex:denoise_ -s 2 -c 2 -f -o $OUT/prof_denoise python tools/denoise_probe.py --once > $OUT/ncu_denoise.log 2>&1 ;;
     denoise)    timeout 600 python tools/denoise_probe.py > $OUT/denoise_probe.txt 2>&1; tail -12 $OUT/denoise_probe.txt ;;
     timeline)   timeout 600 python tools/timeline_probe.py > $OUT/timeline.txt 2>&1 ;;
