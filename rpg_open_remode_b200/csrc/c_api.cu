@@ -114,6 +114,7 @@ int rmd_debug_host_profile(double out[8], int reset)
 // =========================================================== seed matrix
 
 static const int kSlots = 3;
+static const int kStatsSlots = 4, kStatsEvery = 8, kStatsLag = 16;
 
 struct rmd_seeds
 {
@@ -176,8 +177,13 @@ struct rmd_seeds
   unsigned int *seed_ctl;      // 8 uints, see SeedModeBatch
   int seed_cur, seed_est;      // list in use; host-side upper bound of its length
   int seed_mode_pct;           // go seed-major when at most this percentage of the pixels is still updated (0 = never)
-  unsigned int *host_stats;    // pinned: the last frame's work-list counters, copied back asynchronously
-  cudaEvent_t stats_ev; bool stats_pending;
+  // The host enqueues frames far ahead of the GPU, so the statistics that decide the switch are requested
+  // every kStatsEvery frames into a small ring and READ WITH A LAG: the host looks at a request as soon as it
+  // has completed, and waits for it once it is kStatsLag frames old (the GPU then still has that many frames
+  // queued, so it never idles; the host merely stops running further ahead).
+  unsigned int *host_stats;    // pinned, kStatsSlots x 8: a frame's work-list counters
+  cudaEvent_t stats_ev[4]; bool stats_used[4]; uint64_t stats_frame[4];
+  int stats_next; uint64_t stats_last_req;
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
@@ -250,8 +256,9 @@ int seeds_alloc(rmd_seeds *s)
       RMD_CUDA_TRY(cudaMalloc(&s->seed_list[i], sizeof(unsigned int) * (size_t)w * h));
     RMD_CUDA_TRY(cudaMalloc(&s->seed_ctl, 8 * sizeof(unsigned int)));
     RMD_CUDA_TRY(cudaMemset(s->seed_ctl, 0, 8 * sizeof(unsigned int)));
-    RMD_CUDA_TRY(cudaHostAlloc(&s->host_stats, 8 * sizeof(unsigned int), cudaHostAllocDefault));
-    RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->stats_ev, cudaEventDisableTiming));
+    RMD_CUDA_TRY(cudaHostAlloc(&s->host_stats, kStatsSlots * 8 * sizeof(unsigned int), cudaHostAllocDefault));
+    for(int i = 0; i < kStatsSlots; ++i)
+      RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->stats_ev[i], cudaEventDisableTiming));
     RMD_CUDA_TRY(cudaMalloc(&s->chain_state, sizeof(unsigned int) * (size_t)(s->n_tiles + 1)));
     RMD_CUDA_TRY(cudaMemset(s->chain_state, 0, sizeof(unsigned int) * (size_t)(s->n_tiles + 1)));
   }
@@ -287,7 +294,8 @@ void seeds_free(rmd_seeds *s)
   delete[] s->chain_maps;
   cudaFree(s->seed_list[0]); cudaFree(s->seed_list[1]); cudaFree(s->seed_ctl);
   if(s->host_stats) cudaFreeHost(s->host_stats);
-  if(s->stats_ev) cudaEventDestroy(s->stats_ev);
+  for(int i = 0; i < kStatsSlots; ++i)
+    if(s->stats_ev[i]) cudaEventDestroy(s->stats_ev[i]);
   if(s->t0) cudaEventDestroy(s->t0);
   if(s->t1) cudaEventDestroy(s->t1);
   delete s->maps;
@@ -368,7 +376,8 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   s->n_total += 1;
   s->has_reference = true;
   s->mode = 0;            // a new keyframe starts tile-organised; pending statistics belong to the old one
-  s->stats_pending = false;
+  for(int i = 0; i < kStatsSlots; ++i) s->stats_used[i] = false;
+  s->stats_last_req = 0;
   s->frame_index = 0;
   s->trust_conv = true;
   s->dist_from_ref = 0.0f;
@@ -480,26 +489,38 @@ bool seed_mode_allowed(const rmd_seeds *s)
 // compact list of live seeds from the convergence map and continue seed-major (depth_filter_seeds.cu).
 int maybe_enter_seed_mode(rmd_seeds *s)
 {
-  if(s->mode != 0 || !seed_mode_allowed(s) || !s->stats_pending)
+  if(s->mode != 0 || !seed_mode_allowed(s))
     return 0;
-  if(cudaEventQuery(s->stats_ev) != cudaSuccess)
+  for(int n = 0; n < kStatsSlots; ++n)
   {
-    cudaGetLastError();
+    const int slot = (s->stats_next + n) % kStatsSlots;    // oldest request first
+    if(!s->stats_used[slot])
+      continue;
+    bool done = (cudaEventQuery(s->stats_ev[slot]) == cudaSuccess);
+    if(!done)
+    {
+      cudaGetLastError();
+      if(s->frame_index - s->stats_frame[slot] < (uint64_t)kStatsLag)
+        break;                                              // younger requests are not done either
+      RMD_CUDA_TRY(cudaEventSynchronize(s->stats_ev[slot]));
+      done = true;
+    }
+    s->stats_used[slot] = false;
+    const unsigned int active = s->host_stats[8 * slot + 7];
+    const size_t pixels = (size_t)s->width * s->height;
+    if((size_t)active * 100 > pixels * (size_t)s->seed_mode_pct)
+      continue;
+    for(int i = 0; i < kStatsSlots; ++i) s->stats_used[i] = false;
+    RMD_CUDA_TRY(cudaMemsetAsync(s->seed_ctl, 0, 8 * sizeof(unsigned int), s->stream));
+    RMD_CUDA_TRY(launch_seed_list_build(s->conv, (int)(s->conv_pitch / sizeof(int)), s->width, s->height,
+                                        s->seed_list[0], s->seed_ctl, s->stream));
+    s->n_total += 1;
+    s->seed_cur = 0;
+    s->seed_est = (int)active;    // the live set only shrinks: an upper bound from now on
+    s->mode = 1;
+    s->worklist_valid = false;    // the tile work list is not maintained while seed-major
     return 0;
   }
-  s->stats_pending = false;
-  const unsigned int active = s->host_stats[7];
-  const size_t pixels = (size_t)s->width * s->height;
-  if((size_t)active * 100 > pixels * (size_t)s->seed_mode_pct)
-    return 0;
-  RMD_CUDA_TRY(cudaMemsetAsync(s->seed_ctl, 0, 8 * sizeof(unsigned int), s->stream));
-  RMD_CUDA_TRY(launch_seed_list_build(s->conv, (int)(s->conv_pitch / sizeof(int)), s->width, s->height,
-                                      s->seed_list[0], s->seed_ctl, s->stream));
-  s->n_total += 1;
-  s->seed_cur = 0;
-  s->seed_est = (int)active;    // the live set only shrinks: an upper bound from now on
-  s->mode = 1;
-  s->worklist_valid = false;    // the tile work list is not maintained while seed-major
   return 0;
 }
 
@@ -511,17 +532,25 @@ void leave_seed_mode(rmd_seeds *s)
     s->mode = 0;
     s->worklist_valid = false;
   }
-  s->stats_pending = false;
+  for(int i = 0; i < kStatsSlots; ++i) s->stats_used[i] = false;
+  s->stats_last_req = 0;
 }
 
 // Tile mode, after a frame's launch: ask for its statistics (asynchronously; one request in flight).
-int request_stats(rmd_seeds *s, const FilterParams &P)
+int request_stats(rmd_seeds *s, const FilterParams &P, cudaStream_t stream)
 {
-  if(s->mode != 0 || !seed_mode_allowed(s) || s->stats_pending)
+  if(s->mode != 0 || !seed_mode_allowed(s))
     return 0;
-  RMD_CUDA_TRY(cudaMemcpyAsync(s->host_stats, P.counts_next, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
-  RMD_CUDA_TRY(cudaEventRecord(s->stats_ev, s->stream));
-  s->stats_pending = true;
+  if(s->stats_last_req != 0 && s->frame_index - s->stats_last_req < (uint64_t)kStatsEvery)
+    return 0;
+  const int slot = s->stats_next;      // (an unread request of kStatsSlots requests ago is simply superseded)
+  RMD_CUDA_TRY(cudaMemcpyAsync(s->host_stats + 8 * slot, P.counts_next, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                               stream));
+  RMD_CUDA_TRY(cudaEventRecord(s->stats_ev[slot], stream));
+  s->stats_used[slot] = true;
+  s->stats_frame[slot] = s->frame_index;
+  s->stats_next = (slot + 1) % kStatsSlots;
+  s->stats_last_req = s->frame_index;
   return 0;
 }
 
@@ -581,7 +610,7 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     s->t_valid = true;
   }
   finish_update(s);
-  return request_stats(s, P);
+  return request_stats(s, P, s->stream);
 }
 
 // rmd::Depthmap::inputImage (src/depthmap.cpp:95-106) for a frame already on the
@@ -984,14 +1013,8 @@ int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t
     {
       rmd_seeds *h = handles[batch_ids[g + k]];
       finish_update(h);
-      if(!h->stats_pending && seed_mode_allowed(h))
-      {
-        // statistics of this frame, on the stream the batch ran on
-        RMD_CUDA_TRY(cudaMemcpyAsync(h->host_stats, P[k].counts_next, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost,
-                                     h0->stream));
-        RMD_CUDA_TRY(cudaEventRecord(h->stats_ev, h0->stream));
-        h->stats_pending = true;
-      }
+      const int rcs = request_stats(h, P[k], h0->stream);    // on the stream the batch ran on
+      if(rcs) return rcs;
     }
   }
   for(int j = 0; j < n_single; ++j)
@@ -1252,7 +1275,7 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
     s->n_fused -= (uint64_t)(m - 1);   // launch counters count launches, not frames
     s->n_total -= (uint64_t)(m - 1);
     {
-      const int rc = request_stats(s, P[m - 1]);
+      const int rc = request_stats(s, P[m - 1], s->stream);
       if(rc) return rc;
     }
     i += m;
