@@ -105,9 +105,11 @@ enum rmd_seeds_option {
    * are chained inside ONE persistent launch -- a tile moves on to frame k+1 as soon as its own frame k is
    * final, so frames overlap on the GPU.  Same results as one launch per frame (1). */
   RMD_OPT_CHAIN_FRAMES = 5,
-  /* Seed-major mode: once at most this percentage of the pixels is still being updated (default 8; 0 = never)
+  /* Seed-major mode: once at most this percentage of the pixels is still being updated (0 = never, the default)
    * the handle keeps the live seeds as a compact list and a launch walks every listed seed through its frames
-   * warp by warp -- no tiles, no per-frame synchronisation (csrc/depth_filter_seeds.cu).  Same results. */
+   * warp by warp -- no tiles, no per-frame synchronisation (csrc/depth_filter_seeds.cu).  Same results.  Off by
+   * default: on the bench workloads 10-20 % of the seeds stay live (NO_MATCH seeds keep searching) and at that
+   * density the tile organisation is faster (profiles/r02_tune_probe.txt); it pays for sparser live sets. */
   RMD_OPT_SEED_MODE_PCT = 6,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */

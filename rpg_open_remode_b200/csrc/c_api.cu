@@ -773,7 +773,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[7] = staged::WARP_TILE_MAX_SEEDS;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
   s->chain_frames = STAGED_BATCH_MAX;
-  s->seed_mode_pct = 8;
+  s->seed_mode_pct = 0;   // off by default: measured slower than the tile organisation on the bench workloads
   const int rc = seeds_alloc(s);
   if(rc)
   {

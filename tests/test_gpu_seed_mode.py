@@ -45,13 +45,13 @@ def test_seed_mode_equals_tile_mode_and_direct(patch, size, n):
     tile = _new(seq, f0, dmin, dmax, pct=0, patch=patch)
     early = _new(seq, f0, dmin, dmax, pct=100, patch=patch)     # seed-major from the third or fourth frame on
     mid = _new(seq, f0, dmin, dmax, pct=30, patch=patch)
-    dflt = _new(seq, f0, dmin, dmax, patch=patch)
+    dflt = _new(seq, f0, dmin, dmax, pct=8, patch=patch)
     for k in range(1, n):
         for g in (ref, tile, early, mid, dflt):
             g.update(frames[k].image, frames[k].T_cam_world)
         if k in (3, 8, 20, n // 2, n - 1):
             R = _snap(ref)
-            for name, g in (("tile", tile), ("seed-major from the start", early), ("seed-major at 30 %", mid), ("default", dflt)):
+            for name, g in (("tile", tile), ("seed-major from the start", early), ("seed-major at 30 %", mid), ("seed-major at 8 %", dflt)):
                 _same(_snap(g), R, f"{name}, frame {k}")
                 assert g.getConvergedCount() == ref.getConvergedCount() == int((R["conv"] == 1).sum()), (name, k)
     assert early.launchCount()[0] == n - 1
