@@ -942,8 +942,14 @@ __device__ __forceinline__ void process_warp_tile(const FilterParams &P, StagedS
 // with nothing left to update, ever, are not listed.  K > 1: the lists of up to K keyframes (independent
 // reference views updated by the same incoming frame) are concatenated -- all heavy lists, then all light
 // lists -- so the dependent chains of different keyframes interleave from the first cycle.
+// CTAs per SM the register budget is sized for (5x5 patch: 3 x 256 threads x 80 registers; tools/build_variant_lib.sh
+// builds the 2-CTA / 128-register alternative for the A/B in profiles/r02_tune_probe.txt)
+#ifndef RMD_STAGED_P5_MIN_BLOCKS
+#define RMD_STAGED_P5_MIN_BLOCKS 3
+#endif
+
 template<int PS, int K>
-__global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? 3 : 2)) depth_filter_staged_kernel(
+__global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? RMD_STAGED_P5_MIN_BLOCKS : 2)) depth_filter_staged_kernel(
     const __grid_constant__ StagedBatch<K> B)
 {
   extern __shared__ unsigned char smem_raw[];
