@@ -111,6 +111,14 @@ enum rmd_seeds_option {
    * default: on the bench workloads 10-20 % of the seeds stay live (NO_MATCH seeds keep searching) and at that
    * density the tile organisation is faster (profiles/r02_tune_probe.txt); it pays for sparser live sets. */
   RMD_OPT_SEED_MODE_PCT = 6,
+  /* Host frames (rmd_seeds_update / _u8) per launch, 1..8 (default 1).  With a group of g > 1 a frame is copied
+   * and uploaded when it is handed over, but its kernel waits until g frames are there and then ONE chained
+   * launch (RMD_OPT_CHAIN_FRAMES) covers them.  Every other entry point -- sync, downloads, converged_count,
+   * set_reference, the denoiser, get_stream ... -- first launches what is waiting, so results and the order of
+   * effects are those of g = 1; only the launch count and the moment a frame starts to be processed change.
+   * A caller that hands over frames faster than the GPU filters them (replay, the bench) wins the chained
+   * kernel's frame overlap; a live 30 Hz camera should leave it at 1 (it would add g-1 frame times of latency). */
+  RMD_OPT_HOST_FRAME_GROUP = 7,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */
   RMD_OPT_TUNE_SPLIT_MAX = 10,            /* most CTAs sharing one busy tile (1 = never split; default 16) */
@@ -120,7 +128,8 @@ enum rmd_seeds_option {
   RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14,      /* tiles with at least this many items are dispatched first (32) */
   RMD_OPT_TUNE_SPLIT_AVG_PCT = 15,        /* target items per CTA of a split tile, in % of the frame's items per resident CTA slot (100) */
   RMD_OPT_TUNE_PDL = 16,           /* 1 (default): programmatic dependent launch of consecutive frames */
-  RMD_OPT_TUNE_WARP_TILE_SEEDS = 17 /* tiles with at most this many seeds to update (and a few dozen candidates) are processed by one warp, eight per CTA (8; 0 = off) */
+  RMD_OPT_TUNE_WARP_TILE_SEEDS = 17, /* tiles with at most this many seeds to update (and a few dozen candidates) are processed by one warp, eight per CTA (8; 0 = off) */
+  RMD_OPT_TUNE_GRID_CTAS = 18       /* size of the persistent grid (0, the default: one CTA per resident slot, SMs x occupancy) */
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

@@ -113,7 +113,15 @@ int rmd_debug_host_profile(double out[8], int reset)
 
 // =========================================================== seed matrix
 
-static const int kSlots = 3;
+// Every entry point that looks at, or orders work after, the seed state first launches the host frames whose
+// kernel RMD_OPT_HOST_FRAME_GROUP deferred.
+#define RMD_FLUSH(s)                                         \
+  do {                                                       \
+    const int rmd_flush_rc_ = flush_pending(s);              \
+    if(rmd_flush_rc_) return rmd_flush_rc_;                  \
+  } while(0)
+
+static const int kSlots = 12;     // ring capacity; ring_size of them are in use (3 unless frames are grouped)
 static const int kStatsSlots = 4, kStatsEvery = 8, kStatsLag = 16;
 
 struct rmd_seeds
@@ -134,7 +142,13 @@ struct rmd_seeds
   void *pinned[kSlots];
   cudaEvent_t copied[kSlots], consumed[kSlots];
   bool slot_used[kSlots];
-  int next_slot;
+  int next_slot, ring_size;
+  // RMD_OPT_HOST_FRAME_GROUP: host frames are uploaded at once but their kernel is deferred until
+  // `host_group` of them wait, then ONE chained launch covers them (flush_pending; every other entry point
+  // flushes first, so nothing observable changes but the launch count)
+  int host_group, n_pending;
+  int pend_slot[STAGED_BATCH_MAX];
+  float pend_pose[12 * STAGED_BATCH_MAX];
 
   float2 *matches; size_t matches_pitch;
   float *planar[6]; size_t planar_pitch;   // mu, sigma_sq, a, b, sum_templ, denom
@@ -187,7 +201,7 @@ struct rmd_seeds
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  int tune[8];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds
+  int tune[9];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds, grid_ctas
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
   // lens undistortion of 8-bit frames (ingest.cuh); maps are null until init_undistortion_map
   short2 *undist_xy; uint16_t *undist_frac;
@@ -206,6 +220,21 @@ struct rmd_seeds
 namespace
 {
 
+int flush_pending(rmd_seeds *s);
+
+// Ring slot i: device image, pinned staging buffer, events (the first three at creation, the others when
+// RMD_OPT_HOST_FRAME_GROUP widens the ring).
+int ensure_slot(rmd_seeds *s, int i)
+{
+  if(s->curr[i]) return 0;
+  const int w = s->width, h = s->height;
+  RMD_CUDA_TRY(cudaMallocPitch(&s->curr[i], &s->curr_pitch, sizeof(float) * (size_t)w, h));
+  RMD_CUDA_TRY(cudaHostAlloc(&s->pinned[i], sizeof(float) * (size_t)w * h, cudaHostAllocDefault));
+  RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
+  RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
+  return 0;
+}
+
 int seeds_alloc(rmd_seeds *s)
 {
   const int w = s->width, h = s->height;
@@ -218,12 +247,10 @@ int seeds_alloc(rmd_seeds *s)
   RMD_CUDA_TRY(cudaMalloc(&s->templ, sizeof(float2) * (size_t)s->templ_stride * h));
   RMD_CUDA_TRY(cudaMallocPitch(&s->conv, &s->conv_pitch, sizeof(int) * (size_t)w, h));
   RMD_CUDA_TRY(cudaMallocPitch(&s->ref, &s->ref_pitch, sizeof(float) * (size_t)w, h));
-  for(int i = 0; i < kSlots; ++i)
+  for(int i = 0; i < 3; ++i)
   {
-    RMD_CUDA_TRY(cudaMallocPitch(&s->curr[i], &s->curr_pitch, sizeof(float) * (size_t)w, h));
-    RMD_CUDA_TRY(cudaHostAlloc(&s->pinned[i], sizeof(float) * (size_t)w * h, cudaHostAllocDefault));
-    RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->copied[i], cudaEventDisableTiming));
-    RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->consumed[i], cudaEventDisableTiming));
+    const int rc = ensure_slot(s, i);
+    if(rc) return rc;
   }
   RMD_CUDA_TRY(cudaEventCreateWithFlags(&s->ext_ev, cudaEventDisableTiming));
   RMD_CUDA_TRY(cudaMalloc(&s->counters, 4 * sizeof(unsigned int)));
@@ -436,6 +463,7 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.light_cur = s->light_list[f % 3]; P.light_next = s->light_list[(f + 1) % 3];
     P.sparse_cur = s->sparse_list[f % 3]; P.sparse_next = s->sparse_list[(f + 1) % 3];
     P.warp_tile_max_seeds = s->tune[7];
+    P.grid_ctas = s->tune[8];
     P.counts_cur = s->work_counts + 8 * (f % 3);
     P.counts_next = s->work_counts + 8 * ((f + 1) % 3);
     P.counts_zero = s->work_counts + 8 * ((f + 2) % 3);
@@ -613,6 +641,107 @@ int enqueue_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
   return request_stats(s, P, s->stream);
 }
 
+// Enqueue n consecutive frames (device pointers, one pitch, poses 12 floats apiece).  Frame chaining: up to
+// chain_frames (<= STAGED_BATCH_MAX) consecutive frames per launch of the staged kernel.  Every tile walks
+// through the frames of a launch on its own (frame k+1 of a tile only needs frame k of that tile), so frames
+// overlap on the GPU and the per-frame launch gap disappears; results are those of one launch per frame.
+int enqueue_frames(rmd_seeds *s, const float *const *frames, size_t pitch_bytes, const float *T_curr_world, int n_frames)
+{
+  const int per_launch = (s->variant == 0 && !s->timeline && !s->timing) ? s->chain_frames : 1;
+  for(int i = 0; i < n_frames; )
+  {
+    if(s->mode == 1 && !seed_mode_allowed(s))
+      leave_seed_mode(s);
+    {
+      const int rc = maybe_enter_seed_mode(s);
+      if(rc) return rc;
+    }
+    if(s->mode == 1)
+    {
+      // seed-major: every listed seed walks through up to SEED_FRAMES_MAX frames inside one launch
+      const int m = (n_frames - i < SEED_FRAMES_MAX) ? n_frames - i : SEED_FRAMES_MAX;
+      const int rc = enqueue_seed_mode(s, frames + i, pitch_bytes, T_curr_world + 12 * i, m);
+      if(rc) return rc;
+      i += m;
+      continue;
+    }
+    const int m = (n_frames - i < per_launch) ? n_frames - i : per_launch;
+    if(m <= 1)
+    {
+      const int rc = enqueue_update(s, frames[i], pitch_bytes, T_curr_world + 12 * i);
+      if(rc) return rc;
+      i += 1;
+      continue;
+    }
+    if(!s->chain_maps) s->chain_maps = new StagedMaps[STAGED_BATCH_MAX];
+    FilterParams P[STAGED_BATCH_MAX];
+    const FilterParams *pp[STAGED_BATCH_MAX];
+    const StagedMaps *mm[STAGED_BATCH_MAX];
+    for(int k = 0; k < m; ++k)
+    {
+      const int rc = prepare_update(s, frames[i + k], pitch_bytes, T_curr_world + 12 * (i + k), P[k], &s->chain_maps[k]);
+      if(rc) return rc;
+      pp[k] = &P[k];
+      mm[k] = &s->chain_maps[k];
+    }
+    {
+      ProfScope prof_launch(4);
+      RMD_CUDA_TRY(launch_depth_filter_staged(pp, mm, m, 1, s->cursor, s->patch, s->stream));
+    }
+    for(int k = 0; k < m; ++k)
+      finish_update(s);
+    s->n_fused -= (uint64_t)(m - 1);   // launch counters count launches, not frames
+    s->n_total -= (uint64_t)(m - 1);
+    {
+      const int rc = request_stats(s, P[m - 1], s->stream);
+      if(rc) return rc;
+    }
+    i += m;
+  }
+  return 0;
+}
+
+// Launch the host frames whose kernel was deferred (RMD_OPT_HOST_FRAME_GROUP) and release their ring slots.
+int flush_pending(rmd_seeds *s)
+{
+  const int n = s->n_pending;
+  if(n == 0) return 0;
+  s->n_pending = 0;
+  DeviceGuard guard(s->device);
+  const float *frames[STAGED_BATCH_MAX];
+  for(int k = 0; k < n; ++k)
+    frames[k] = s->curr[s->pend_slot[k]];
+  const int rc = enqueue_frames(s, frames, s->curr_pitch, s->pend_pose, n);
+  if(rc) return rc;
+  for(int k = 0; k < n; ++k)
+    RMD_CUDA_TRY(cudaEventRecord(s->consumed[s->pend_slot[k]], s->stream));
+  return 0;
+}
+
+// A staged host frame: launch it now, or park it until the group is full.
+int submit_host_frame(rmd_seeds *s, int slot, const float *T_curr_world)
+{
+  if(s->host_group <= 1)
+  {
+    const int rc = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
+    if(rc) return rc;
+    RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
+    return 0;
+  }
+  {
+    // getDistFromRef (seed_matrix.cu:124-125) answers for this frame straight away
+    const Pose T_curr_ref = pose_compose(pose_from(T_curr_world), s->T_world_ref);
+    const float tx = T_curr_ref.m[3], ty = T_curr_ref.m[7], tz = T_curr_ref.m[11];
+    s->dist_from_ref = sqrtf(tx * tx + ty * ty + tz * tz);
+  }
+  s->pend_slot[s->n_pending] = slot;
+  memcpy(s->pend_pose + 12 * s->n_pending, T_curr_world, 12 * sizeof(float));
+  s->n_pending += 1;
+  if(s->n_pending >= s->host_group)
+    return flush_pending(s);
+  return 0;
+}
+
 // rmd::Depthmap::inputImage (src/depthmap.cpp:95-106) for a frame already on the
 // device: remap through the undistortion maps if the camera has them, then
 // 8U -> 32F * (1/255), in one kernel on the compute stream.
@@ -641,8 +770,12 @@ bool is_page_locked(const void *p)
 // compute stream wait for it.  Returns the slot.
 int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *slot_out)
 {
-  const int slot = s->next_slot;
-  s->next_slot = (slot + 1) % kSlots;
+  const int slot = s->next_slot % s->ring_size;
+  s->next_slot = (slot + 1) % s->ring_size;
+  {
+    const int rc = ensure_slot(s, slot);
+    if(rc) return rc;
+  }
   const size_t row_bytes = elem_size * (size_t)s->width;
   // RMD_OPT_PINNED_INPUT: the caller's buffer is page-locked and stays untouched until the next sync,
   // so the DMA reads it in place (no staging copy, no wait for the pinned ring slot)
@@ -773,6 +906,8 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[7] = staged::WARP_TILE_MAX_SEEDS;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
   s->chain_frames = STAGED_BATCH_MAX;
+  s->ring_size = 3;
+  s->host_group = 1;
   s->seed_mode_pct = 0;   // off by default: measured slower than the tile organisation on the bench workloads
   const int rc = seeds_alloc(s);
   if(rc)
@@ -797,6 +932,7 @@ int rmd_seeds_destroy(rmd_seeds_t *s)
 int rmd_seeds_set_stream(rmd_seeds_t *s, void *cuda_stream)
 {
   RMD_REQUIRE(s, "rmd_seeds_set_stream: null handle");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
@@ -806,6 +942,7 @@ int rmd_seeds_set_stream(rmd_seeds_t *s, void *cuda_stream)
 int rmd_seeds_get_stream(rmd_seeds_t *s, void **cuda_stream)
 {
   RMD_REQUIRE(s && cuda_stream, "rmd_seeds_get_stream: null");
+  RMD_FLUSH(s);
   *cuda_stream = (void*)s->stream;
   return 0;
 }
@@ -813,10 +950,16 @@ int rmd_seeds_get_stream(rmd_seeds_t *s, void **cuda_stream)
 int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
 {
   RMD_REQUIRE(s, "rmd_seeds_set_option: null handle");
+  RMD_FLUSH(s);
   switch(option)
   {
   case RMD_OPT_RECORD_MATCHES: s->record_matches = (value != 0); return 0;
   case RMD_OPT_PINNED_INPUT: s->pinned_input = (value != 0); return 0;
+  case RMD_OPT_HOST_FRAME_GROUP:
+    RMD_REQUIRE(value >= 1 && value <= STAGED_BATCH_MAX, "RMD_OPT_HOST_FRAME_GROUP: 1..8");
+    s->host_group = value;
+    s->ring_size = value > 1 ? value + 3 : 3;   // a slot is reused only after its group was launched
+    return 0;
   case RMD_OPT_CHAIN_FRAMES:
     RMD_REQUIRE(value >= 1 && value <= STAGED_BATCH_MAX, "RMD_OPT_CHAIN_FRAMES: 1..8");
     s->chain_frames = value;
@@ -852,9 +995,9 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   }
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
   case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT: case RMD_OPT_TUNE_PDL:
-  case RMD_OPT_TUNE_WARP_TILE_SEEDS:
+  case RMD_OPT_TUNE_WARP_TILE_SEEDS: case RMD_OPT_TUNE_GRID_CTAS:
     RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL ||
-                           option == RMD_OPT_TUNE_WARP_TILE_SEEDS) ? 0 : 1) && value <= 65535, "tuning value out of range");
+                           option == RMD_OPT_TUNE_WARP_TILE_SEEDS || option == RMD_OPT_TUNE_GRID_CTAS) ? 0 : 1) && value <= 65535, "tuning value out of range");
     RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= staged::WARP_TILE_MAX_SEEDS, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..8");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
@@ -871,6 +1014,7 @@ int rmd_seeds_set_reference(rmd_seeds_t *s, const float *host_img, const float *
                             float min_depth, float max_depth)
 {
   RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_set_reference: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t row = sizeof(float) * (size_t)s->width;
   // pageable source: returns once the data is staged, buffer reusable
@@ -883,6 +1027,7 @@ int rmd_seeds_set_reference_device(rmd_seeds_t *s, const float *dev_img, size_t 
                                    const float *T_curr_world, float min_depth, float max_depth)
 {
   RMD_REQUIRE(s && dev_img && T_curr_world, "rmd_seeds_set_reference_device: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t row = sizeof(float) * (size_t)s->width;
   RMD_REQUIRE(pitch_bytes >= row, "rmd_seeds_set_reference_device: pitch smaller than a row");
@@ -895,6 +1040,7 @@ int rmd_seeds_set_reference_u8(rmd_seeds_t *s, const uint8_t *host_img, const fl
                                float min_depth, float max_depth)
 {
   RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_set_reference_u8: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   // own scratch image: the ring slots belong to frames that may still be in flight
   if(!s->ref_u8)
@@ -917,10 +1063,7 @@ int rmd_seeds_update(rmd_seeds_t *s, const float *host_img, const float *T_curr_
   int slot = 0;
   const int rc = stage_host_frame(s, host_img, sizeof(float), &slot);
   if(rc) return rc;
-  const int rc2 = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
-  if(rc2) return rc2;
-  RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
-  return 0;
+  return submit_host_frame(s, slot, T_curr_world);
 }
 
 int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_curr_world)
@@ -934,10 +1077,7 @@ int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_
   int slot = 0;
   const int rc = stage_host_frame(s, host_img, sizeof(uint8_t), &slot);
   if(rc) return rc;
-  const int rc2 = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
-  if(rc2) return rc2;
-  RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
-  return 0;
+  return submit_host_frame(s, slot, T_curr_world);
 }
 
 namespace
@@ -961,6 +1101,8 @@ int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t
   ProfScope prof(5);
   if(g_prof_on) g_prof[6] += 1.0;
   DeviceGuard guard(h0->device);
+  for(int i = 0; i < n; ++i)
+    RMD_FLUSH(handles[i]);
   for(int i = 0; i < n; ++i)
     if(!handles[i]->fan_ev)
       RMD_CUDA_TRY(cudaEventCreateWithFlags(&handles[i]->fan_ev, cudaEventDisableTiming));
@@ -1179,6 +1321,7 @@ int rmd_seeds_point_cloud(rmd_seeds_t *s, const float *dev_depth, size_t depth_p
                           float *host_xyzi, size_t capacity_points, size_t *count)
 {
   RMD_REQUIRE(s && count && (host_xyzi || capacity_points == 0), "rmd_seeds_point_cloud: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   if(!s->pc_points)
     RMD_CUDA_TRY(cudaMalloc(&s->pc_points, sizeof(float4) * (size_t)s->width * s->height));
@@ -1194,6 +1337,7 @@ int rmd_seeds_point_cloud_device(rmd_seeds_t *s, const float *dev_depth, size_t 
                                  float *dev_xyzi, size_t capacity_points, size_t *count)
 {
   RMD_REQUIRE(s && count && (dev_xyzi || capacity_points == 0), "rmd_seeds_point_cloud_device: null argument");
+  RMD_FLUSH(s);
   RMD_REQUIRE(((uintptr_t)dev_xyzi % 16) == 0, "rmd_seeds_point_cloud_device: output must be 16-byte aligned");
   DeviceGuard guard(s->device);
   return point_cloud_run(s, dev_depth, depth_pitch_bytes, reinterpret_cast<float4*>(dev_xyzi), capacity_points, count);
@@ -1203,6 +1347,7 @@ int rmd_seeds_update_device(rmd_seeds_t *s, const float *dev_img, size_t pitch_b
                             const float *T_curr_world)
 {
   RMD_REQUIRE(s && dev_img && T_curr_world, "rmd_seeds_update_device: null argument");
+  RMD_FLUSH(s);
   RMD_REQUIRE(pitch_bytes >= sizeof(float) * (size_t)s->width && pitch_bytes % 16 == 0 &&
               ((uintptr_t)dev_img % 16) == 0,
               "rmd_seeds_update_device: image must be 16-byte aligned with a pitch multiple of 16");
@@ -1223,62 +1368,16 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
   if(!s->has_reference)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_device_batch: set_reference has not been called");
   DeviceGuard guard(s->device);
+  RMD_FLUSH(s);
   const char *base = reinterpret_cast<const char*>(dev_frames);
-  // Frame chaining: up to STAGED_BATCH_MAX consecutive frames per launch of the staged kernel.  Every tile
-  // walks through the frames of a launch on its own (frame k+1 of a tile only needs frame k of that tile), so
-  // frames overlap on the GPU and the per-frame launch gap disappears; results are those of one launch per frame.
-  const int per_launch = (s->variant == 0 && !s->timeline && !s->timing) ? s->chain_frames : 1;
-  for(int i = 0; i < n_frames; )
+  for(int i = 0; i < n_frames; i += SEED_FRAMES_MAX)
   {
-    if(s->mode == 1 && !seed_mode_allowed(s))
-      leave_seed_mode(s);
-    {
-      const int rc = maybe_enter_seed_mode(s);
-      if(rc) return rc;
-    }
-    if(s->mode == 1)
-    {
-      // seed-major: every listed seed walks through up to SEED_FRAMES_MAX frames inside one launch
-      const int m = (n_frames - i < SEED_FRAMES_MAX) ? n_frames - i : SEED_FRAMES_MAX;
-      const float *frames[SEED_FRAMES_MAX];
-      for(int k = 0; k < m; ++k)
-        frames[k] = reinterpret_cast<const float*>(base + (size_t)(i + k) * frame_stride_bytes);
-      const int rc = enqueue_seed_mode(s, frames, pitch_bytes, T_curr_world + 12 * i, m);
-      if(rc) return rc;
-      i += m;
-      continue;
-    }
-    const int m = (n_frames - i < per_launch) ? n_frames - i : per_launch;
-    if(m <= 1)
-    {
-      const int rc = enqueue_update(s, reinterpret_cast<const float*>(base + (size_t)i * frame_stride_bytes), pitch_bytes,
-                                    T_curr_world + 12 * i);
-      if(rc) return rc;
-      i += 1;
-      continue;
-    }
-    if(!s->chain_maps) s->chain_maps = new StagedMaps[STAGED_BATCH_MAX];
-    FilterParams P[STAGED_BATCH_MAX];
-    const FilterParams *pp[STAGED_BATCH_MAX];
-    const StagedMaps *mm[STAGED_BATCH_MAX];
+    const int m = (n_frames - i < SEED_FRAMES_MAX) ? n_frames - i : SEED_FRAMES_MAX;
+    const float *frames[SEED_FRAMES_MAX];
     for(int k = 0; k < m; ++k)
-    {
-      const int rc = prepare_update(s, reinterpret_cast<const float*>(base + (size_t)(i + k) * frame_stride_bytes),
-                                    pitch_bytes, T_curr_world + 12 * (i + k), P[k], &s->chain_maps[k]);
-      if(rc) return rc;
-      pp[k] = &P[k];
-      mm[k] = &s->chain_maps[k];
-    }
-    RMD_CUDA_TRY(launch_depth_filter_staged(pp, mm, m, 1, s->cursor, s->patch, s->stream));
-    for(int k = 0; k < m; ++k)
-      finish_update(s);
-    s->n_fused -= (uint64_t)(m - 1);   // launch counters count launches, not frames
-    s->n_total -= (uint64_t)(m - 1);
-    {
-      const int rc = request_stats(s, P[m - 1], s->stream);
-      if(rc) return rc;
-    }
-    i += m;
+      frames[k] = reinterpret_cast<const float*>(base + (size_t)(i + k) * frame_stride_bytes);
+    const int rc = enqueue_frames(s, frames, pitch_bytes, T_curr_world + 12 * i, m);
+    if(rc) return rc;
   }
   return 0;
 }
@@ -1286,6 +1385,7 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
 int rmd_seeds_sync(rmd_seeds_t *s)
 {
   RMD_REQUIRE(s, "rmd_seeds_sync: null handle");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1299,6 +1399,7 @@ int rmd_seeds_sync(rmd_seeds_t *s)
 int rmd_seeds_download(rmd_seeds_t *s, int field, void *host_dst)
 {
   RMD_REQUIRE(s && host_dst, "rmd_seeds_download: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t w = s->width, h = s->height;
   if(is_seed_field(field) || is_templ_field(field))
@@ -1345,6 +1446,7 @@ int rmd_seeds_download(rmd_seeds_t *s, int field, void *host_dst)
 int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
 {
   RMD_REQUIRE(s && host_src, "rmd_seeds_upload_state: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   {
     const int rc = wait_external(s);
@@ -1381,6 +1483,7 @@ int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
 int rmd_seeds_device_ptr(rmd_seeds_t *s, int field, void **dev_ptr, size_t *pitch_bytes)
 {
   RMD_REQUIRE(s && dev_ptr && pitch_bytes, "rmd_seeds_device_ptr: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   if(field == RMD_FIELD_CONVERGENCE)
   {
@@ -1422,6 +1525,7 @@ int rmd_seeds_device_ptr(rmd_seeds_t *s, int field, void **dev_ptr, size_t *pitc
 int rmd_seeds_copy_field_to_device(rmd_seeds_t *s, int field, void *dev_dst, size_t dst_pitch_bytes)
 {
   RMD_REQUIRE(s && dev_dst, "rmd_seeds_copy_field_to_device: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t w = s->width, h = s->height;
   if(is_seed_field(field) || is_templ_field(field))
@@ -1443,6 +1547,7 @@ int rmd_seeds_copy_field_to_device(rmd_seeds_t *s, int field, void *dev_dst, siz
 int rmd_seeds_converged_count(rmd_seeds_t *s, size_t *count)
 {
   RMD_REQUIRE(s && count, "rmd_seeds_converged_count: null argument");
+  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   if(s->mode == 1)
   {
@@ -1482,6 +1587,7 @@ int rmd_seeds_size(rmd_seeds_t *s, int *width, int *height, int *patch_side)
 int rmd_seeds_launch_count(rmd_seeds_t *s, uint64_t *fused, uint64_t *total)
 {
   RMD_REQUIRE(s, "rmd_seeds_launch_count: null handle");
+  RMD_FLUSH(s);
   if(fused) *fused = s->n_fused;
   if(total) *total = s->n_total;
   return 0;
@@ -1490,6 +1596,7 @@ int rmd_seeds_launch_count(rmd_seeds_t *s, uint64_t *fused, uint64_t *total)
 int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on)
 {
   RMD_REQUIRE(s, "rmd_seeds_enable_kernel_timing: null handle");
+  RMD_FLUSH(s);
   s->timing = (on != 0);
   s->t_valid = false;
   return 0;
@@ -1498,6 +1605,7 @@ int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on)
 int rmd_seeds_last_kernel_ms(rmd_seeds_t *s, float *ms)
 {
   RMD_REQUIRE(s && ms, "rmd_seeds_last_kernel_ms: null argument");
+  RMD_FLUSH(s);
   if(!s->t_valid)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_last_kernel_ms: timing not enabled / no kernel yet");
   DeviceGuard guard(s->device);
@@ -1688,6 +1796,7 @@ int rmd_denoiser_run(rmd_denoiser_t *d, const float *mu, size_t mu_pitch, const 
 
 static int run_seeds_common(rmd_denoiser_t *d, rmd_seeds_t *s, float lambda, int iterations, int *buf)
 {
+  RMD_FLUSH(s);
   if(d->large_sigma_sq < 0.0f)
     return fail(RMD_ERR_NOT_INITIALISED,
                 "rmd_denoiser_run_seeds: set_large_sigma_sq must be called before this function");

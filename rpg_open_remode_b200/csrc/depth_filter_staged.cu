@@ -1234,7 +1234,10 @@ struct StagedLaunch
     if(chain)
       tiles = P[0]->n_tiles + P[0]->helper_cap;   // the frames of a chain share the CTAs
     const dim3 block(TILE_W, NWARPS);
-    const dim3 grid(std::min(n_slots, tiles));   // persistent: never more CTAs than can be resident
+    int ctas = std::min(n_slots, tiles);         // persistent: never more CTAs than can be resident
+    if(P[0]->grid_ctas > 0)
+      ctas = std::min(ctas, P[0]->grid_ctas);
+    const dim3 grid(ctas);
     cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem_bytes(); cfg.stream = stream;
     cudaLaunchAttribute attr[1];
