@@ -745,13 +745,14 @@ int submit_host_frame(rmd_seeds *s, int slot, const float *T_curr_world)
 // rmd::Depthmap::inputImage (src/depthmap.cpp:95-106) for a frame already on the
 // device: remap through the undistortion maps if the camera has them, then
 // 8U -> 32F * (1/255), in one kernel on the compute stream.
-cudaError_t u8_frame_to_float(rmd_seeds *s, const uint8_t *src, size_t src_pitch, float *dst, size_t dst_pitch)
+cudaError_t u8_frame_to_float(rmd_seeds *s, const uint8_t *src, size_t src_pitch, float *dst, size_t dst_pitch,
+                              cudaStream_t stream)
 {
   if(s->undist_xy)
     return launch_undistort_u8(src, (int)src_pitch, s->undist_xy, s->undist_frac, dst,
-                               (int)(dst_pitch / sizeof(float)), NULL, 0, s->width, s->height, s->stream);
+                               (int)(dst_pitch / sizeof(float)), NULL, 0, s->width, s->height, stream);
   return launch_u8_to_float(src, (int)src_pitch, dst, (int)(dst_pitch / sizeof(float)), s->width, s->height,
-                            s->stream);
+                            stream);
 }
 
 // True when `p` lies in page-locked host memory the copy engine can read directly.
@@ -821,13 +822,15 @@ int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *
     RMD_CUDA_TRY(cudaMemcpy2DAsync(s->curr_u8[slot], s->curr_u8_pitch, dma_src, row_bytes,
                                    row_bytes, s->height, cudaMemcpyHostToDevice, s->copy_stream));
   }
-  RMD_CUDA_TRY(cudaEventRecord(s->copied[slot], s->copy_stream));
-  RMD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->copied[slot], 0));
   if(elem_size != sizeof(float))
   {
-    RMD_CUDA_TRY(u8_frame_to_float(s, s->curr_u8[slot], s->curr_u8_pitch, s->curr[slot], s->curr_pitch));
+    // the ingest kernel follows the upload on the COPY stream: it overlaps the filter kernel of the frames
+    // before it, and consecutive filter launches stay back to back on the compute stream
+    RMD_CUDA_TRY(u8_frame_to_float(s, s->curr_u8[slot], s->curr_u8_pitch, s->curr[slot], s->curr_pitch, s->copy_stream));
     s->n_total += 1;
   }
+  RMD_CUDA_TRY(cudaEventRecord(s->copied[slot], s->copy_stream));
+  RMD_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->copied[slot], 0));
   s->slot_used[slot] = true;
   *slot_out = slot;
   return 0;
@@ -1047,7 +1050,7 @@ int rmd_seeds_set_reference_u8(rmd_seeds_t *s, const uint8_t *host_img, const fl
     RMD_CUDA_TRY(cudaMallocPitch(&s->ref_u8, &s->ref_u8_pitch, (size_t)s->width, s->height));
   RMD_CUDA_TRY(cudaMemcpy2DAsync(s->ref_u8, s->ref_u8_pitch, host_img, (size_t)s->width,
                                  (size_t)s->width, s->height, cudaMemcpyHostToDevice, s->stream));
-  RMD_CUDA_TRY(u8_frame_to_float(s, s->ref_u8, s->ref_u8_pitch, s->ref, s->ref_pitch));
+  RMD_CUDA_TRY(u8_frame_to_float(s, s->ref_u8, s->ref_u8_pitch, s->ref, s->ref_pitch, s->stream));
   s->n_total += 1;
   return finish_set_reference(s, T_curr_world, min_depth, max_depth);
 }
@@ -1214,7 +1217,8 @@ int rmd_seeds_init_undistortion_map(rmd_seeds_t *s, float k1, float k2, float r1
     RMD_CUDA_TRY(cudaMalloc(&xy, n * sizeof(short2)));
     RMD_CUDA_TRY(cudaMalloc(&frac, n * sizeof(uint16_t)));
   }
-  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));   // frames in flight still use the previous maps
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));   // frames in flight still use the previous maps
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   RMD_CUDA_TRY(cudaMemcpy(xy, s->undist_host_xy, n * sizeof(short2), cudaMemcpyHostToDevice));
   RMD_CUDA_TRY(cudaMemcpy(frac, s->undist_host_frac, n * sizeof(uint16_t), cudaMemcpyHostToDevice));
   s->undist_xy = xy;
@@ -1226,6 +1230,7 @@ int rmd_seeds_clear_undistortion_map(rmd_seeds_t *s)
 {
   RMD_REQUIRE(s, "rmd_seeds_clear_undistortion_map: null handle");
   DeviceGuard guard(s->device);
+  RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));   // the ingest kernels run there
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   cudaFree(s->undist_xy); cudaFree(s->undist_frac);
   s->undist_xy = NULL; s->undist_frac = NULL;
