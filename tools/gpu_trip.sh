@@ -25,6 +25,8 @@ for stage in "$@"; do
                   RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 300 python tools/tune_probe.py 16,512,384,16,32,100,1,8,8,0,0 16,512,384,16,32,100,1,8,8,0,296 16,512,384,16,32,100,1,8,8,0,222 16,512,384,16,32,100,1,8,8,0,148 16,512,384,16,32,100,1,8,1,0,296 16,512,384,16,32,100,1,8,1,0,222 16,512,384,16,32,100,1,8,1,0,148 2>&1 | tail -n 7; done ;;
     group_probe) for g in 1 2 4 8; do timeout 600 python bench.py --host-group $g --no-cpu-baseline > $OUT/bench_c2_group$g.json 2> $OUT/bench_c2_group$g.err
                   python -c "import json; r=json.loads(open('$OUT/bench_c2_group$g.json').read()); print('host group $g: value', round(r['value']), 'ms', r['ms_per_step'], 'e2e', round(r['e2e']['value']), r['e2e'].get('ms_per_step'))"; done ;;
+    ab_720p)    for lib in librmd_b200.so build/librmd_b200_mb2.so; do echo "library $lib, 1280x720 x 300 frames:"
+                  RMD_PROBE_SIZE=1280,720,300 RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 600 python tools/tune_probe.py 16,512,384,16,32,100,1,8,8,0 16,512,384,16,32,100,1,8,1,0 2>&1 | tail -n 2; done ;;
     ab_mb2)     for lib in librmd_b200.so build/librmd_b200_mb2.so; do export RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib; echo "library $lib:"
                   for g in 1 8; do timeout 600 python bench.py --host-group $g --no-cpu-baseline > $OUT/ab.json 2> $OUT/ab.err
                     python -c "import json; r=json.loads(open('$OUT/ab.json').read()); print('  c2 host group $g: value', round(r['value']), 'ms', round(r['ms_per_step'],3), 'e2e', round(r['e2e']['value']), round(r['e2e'].get('ms_per_step',0),3))"; done

@@ -7,7 +7,7 @@ import torch
 import rpg_open_remode_b200 as rmd
 from rpg_open_remode_b200 import synth
 
-W, H, N = 640, 480, 200
+W, H, N = (int(v) for v in os.environ.get('RMD_PROBE_SIZE', '640,480,200').split(','))
 seq = synth.SyntheticSequence(W, H, seed=0x5EED0002)
 frames = np.empty((N, H, W), np.float32); poses = np.empty((N, 12), np.float32)
 for k in range(N):
@@ -15,7 +15,7 @@ for k in range(N):
     if k == 0: dmin, dmax = float(f.depth.min()), float(f.depth.max())
 dev = torch.device("cuda", 0); stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
 d_frames = torch.from_numpy(frames).to(dev)
-g = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera)); g.setStream(stream.cuda_stream); g.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED)
+g = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera), patch_side=int(os.environ.get('RMD_PROBE_PATCH', '5'))); g.setStream(stream.cuda_stream); g.setOption(rmd.OPT_KERNEL_VARIANT, rmd.VARIANT_STAGED)
 
 def run(cfg):
     cfg = tuple(cfg) + (0,) * (11 - len(cfg))
@@ -43,5 +43,5 @@ if len(sys.argv) > 1:
     CONFIGS = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 for cfg in CONFIGS:
     tot, seg = run(cfg)
-    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d pdl %d warp_tiles %d chain %d seed_pct %d grid %d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-199 %.2f ms" %
-          (*(tuple(cfg) + (0,) * (11 - len(cfg))), tot, 199 / tot * 1e3, *seg), flush=True)
+    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d pdl %d warp_tiles %d chain %d seed_pct %d grid %d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-end %.2f ms" %
+          (*(tuple(cfg) + (0,) * (11 - len(cfg))), tot, (N - 1) / tot * 1e3, *seg), flush=True)
