@@ -81,8 +81,6 @@ def parse_args():
     ap.add_argument("--variant", default=None, choices=[None, "staged", "direct"])
     ap.add_argument("--chain-frames", type=int, default=None,
                     help="frames per chained launch of the device-resident path (RMD_OPT_CHAIN_FRAMES, 1..8; default: the library's)")
-    ap.add_argument("--host-group", type=int, default=None,
-                    help="host frames per launch on the end-to-end path (RMD_OPT_HOST_FRAME_GROUP, 1..8; default: the library's)")
     ap.add_argument("--seed-mode-pct", type=int, default=None,
                     help="RMD_OPT_SEED_MODE_PCT: go seed-major when at most this percentage of the pixels is still updated")
     ap.add_argument("--cpu-frames", type=int, default=30,
@@ -319,8 +317,6 @@ def run_ours(args, rank, world, local_rank):
         seeds.setOption(rmd.OPT_CHAIN_FRAMES, args.chain_frames)
     if args.seed_mode_pct is not None:
         seeds.setOption(rmd.OPT_SEED_MODE_PCT, args.seed_mode_pct)
-    if args.host_group:
-        seeds.setOption(rmd.OPT_HOST_FRAME_GROUP, args.host_group)
     # A dedicated (non-default) torch stream is made current and handed to the handles, so the fused
     # kernels, the denoiser, torch's NCCL calls and the CUDA events that time them are all on one stream.
     stream = torch.cuda.Stream(dev)
@@ -477,7 +473,7 @@ def run_ours(args, rank, world, local_rank):
                    "name": args.config,
                    "parallelism": f"{world} independent keyframes, NCCL gather of final depth+convergence",
                    "kernel_variant": variant,
-                   "frames_per_launch_resident": args.chain_frames or 8,
+                   "frames_per_launch_resident": args.chain_frames or 1,
                    "l2": "inputs larger than L2: %d distinct frames = %.0f MB streamed per step; seed state "
                          "(%.1f MB) is L2-resident by design" % (NF, NF * frame_bytes / 1e6, 28 * W * H / 1e6),
                    "final_state_hist[update,converged,border,diverged,no_match,not_visible]": conv_hist},

@@ -101,9 +101,11 @@ enum rmd_seeds_option {
    * (device_image.cuh:93-106) no longer holds for such buffers.  Pageable
    * buffers still take the staged path.  Default 0. */
   RMD_OPT_PINNED_INPUT = 4,
-  /* Frames per launch of rmd_seeds_update_device_batch (1..8, default 8): consecutive frames of the keyframe
-   * are chained inside ONE persistent launch -- a tile moves on to frame k+1 as soon as its own frame k is
-   * final, so frames overlap on the GPU.  Same results as one launch per frame (1). */
+  /* Frames per launch of rmd_seeds_update_device_batch (1..8, default 1): with n > 1, n consecutive frames of
+   * the keyframe are chained inside ONE persistent launch -- a tile moves on to frame k+1 as soon as its own
+   * frame k is final, so frames overlap on the GPU.  Same results as one launch per frame.  Opt-in: it paid
+   * 9 % with the 80-register kernel at VGA, nothing with the 128-register kernel that is now the default, and it
+   * costs 8-25 % at 720p / 1080p (profiles/r02_occupancy_ab.txt). */
   RMD_OPT_CHAIN_FRAMES = 5,
   /* Seed-major mode: once at most this percentage of the pixels is still being updated (0 = never, the default)
    * the handle keeps the live seeds as a compact list and a launch walks every listed seed through its frames
@@ -111,14 +113,6 @@ enum rmd_seeds_option {
    * default: on the bench workloads 10-20 % of the seeds stay live (NO_MATCH seeds keep searching) and at that
    * density the tile organisation is faster (profiles/r02_tune_probe.txt); it pays for sparser live sets. */
   RMD_OPT_SEED_MODE_PCT = 6,
-  /* Host frames (rmd_seeds_update / _u8) per launch, 1..8 (default 1).  With a group of g > 1 a frame is copied
-   * and uploaded when it is handed over, but its kernel waits until g frames are there and then ONE chained
-   * launch (RMD_OPT_CHAIN_FRAMES) covers them.  Every other entry point -- sync, downloads, converged_count,
-   * set_reference, the denoiser, get_stream ... -- first launches what is waiting, so results and the order of
-   * effects are those of g = 1; only the launch count and the moment a frame starts to be processed change.
-   * A caller that hands over frames faster than the GPU filters them (replay, the bench) wins the chained
-   * kernel's frame overlap; a live 30 Hz camera should leave it at 1 (it would add g-1 frame times of latency). */
-  RMD_OPT_HOST_FRAME_GROUP = 7,
   /* tuning knobs of the staged kernel's busy-tile splitting and sparse-tile
    * path (defaults in csrc/staged_maps.cuh); results never depend on them */
   RMD_OPT_TUNE_SPLIT_MAX = 10,            /* most CTAs sharing one busy tile (1 = never split; default 16) */
@@ -129,7 +123,8 @@ enum rmd_seeds_option {
   RMD_OPT_TUNE_SPLIT_AVG_PCT = 15,        /* target items per CTA of a split tile, in % of the frame's items per resident CTA slot (100) */
   RMD_OPT_TUNE_PDL = 16,           /* 1 (default): programmatic dependent launch of consecutive frames */
   RMD_OPT_TUNE_WARP_TILE_SEEDS = 17, /* tiles with at most this many seeds to update (and a few dozen candidates) are processed by one warp, eight per CTA (8; 0 = off) */
-  RMD_OPT_TUNE_GRID_CTAS = 18       /* size of the persistent grid (0, the default: one CTA per resident slot, SMs x occupancy) */
+  RMD_OPT_TUNE_GRID_CTAS = 18,      /* size of the persistent grid (0, the default: one CTA per resident slot, SMs x occupancy) */
+  RMD_OPT_TUNE_CTAS_PER_SM = 19     /* 5x5 staged kernel: 3 CTAs x 80 registers or 2 CTAs x 128 registers per SM (0, the default: 2) */
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

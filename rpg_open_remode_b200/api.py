@@ -36,12 +36,13 @@ class ConvergenceStates:
 FIELD_MU, FIELD_SIGMA_SQ, FIELD_A, FIELD_B, FIELD_CONVERGENCE = 0, 1, 2, 3, 4
 FIELD_SUM_TEMPL, FIELD_CONST_TEMPL_DENOM, FIELD_EPIPOLAR_MATCHES, FIELD_REF_IMG = 5, 6, 7, 8
 OPT_RECORD_MATCHES, OPT_KERNEL_VARIANT, OPT_TEX_FRAC_BITS, OPT_DEBUG_TIMELINE, OPT_PINNED_INPUT = 0, 1, 2, 3, 4
-OPT_CHAIN_FRAMES, OPT_SEED_MODE_PCT, OPT_HOST_FRAME_GROUP = 5, 6, 7
+OPT_CHAIN_FRAMES, OPT_SEED_MODE_PCT = 5, 6
 # tuning knobs of the staged kernel (include/rmd_b200.h RMD_OPT_TUNE_*; results never depend on them)
 (OPT_TUNE_SPLIT_MAX, OPT_TUNE_SPLIT_MIN_ITEMS, OPT_TUNE_SPLIT_ITEMS_PER_CTA, OPT_TUNE_SPARSE_MAX_SEEDS,
  OPT_TUNE_HEAVY_MIN_ITEMS, OPT_TUNE_SPLIT_AVG_PCT, OPT_TUNE_PDL) = 10, 11, 12, 13, 14, 15, 16
 OPT_TUNE_WARP_TILE_SEEDS = 17
 OPT_TUNE_GRID_CTAS = 18
+OPT_TUNE_CTAS_PER_SM = 19
 FIELD_DEBUG_TIMELINE = 100
 VARIANT_STAGED, VARIANT_DIRECT = 0, 1
 

@@ -113,15 +113,8 @@ int rmd_debug_host_profile(double out[8], int reset)
 
 // =========================================================== seed matrix
 
-// Every entry point that looks at, or orders work after, the seed state first launches the host frames whose
-// kernel RMD_OPT_HOST_FRAME_GROUP deferred.
-#define RMD_FLUSH(s)                                         \
-  do {                                                       \
-    const int rmd_flush_rc_ = flush_pending(s);              \
-    if(rmd_flush_rc_) return rmd_flush_rc_;                  \
-  } while(0)
 
-static const int kSlots = 12;     // ring capacity; ring_size of them are in use (3 unless frames are grouped)
+static const int kSlots = 3;
 static const int kStatsSlots = 4, kStatsEvery = 8, kStatsLag = 16;
 
 struct rmd_seeds
@@ -142,13 +135,7 @@ struct rmd_seeds
   void *pinned[kSlots];
   cudaEvent_t copied[kSlots], consumed[kSlots];
   bool slot_used[kSlots];
-  int next_slot, ring_size;
-  // RMD_OPT_HOST_FRAME_GROUP: host frames are uploaded at once but their kernel is deferred until
-  // `host_group` of them wait, then ONE chained launch covers them (flush_pending; every other entry point
-  // flushes first, so nothing observable changes but the launch count)
-  int host_group, n_pending;
-  int pend_slot[STAGED_BATCH_MAX];
-  float pend_pose[12 * STAGED_BATCH_MAX];
+  int next_slot;
 
   float2 *matches; size_t matches_pitch;
   float *planar[6]; size_t planar_pitch;   // mu, sigma_sq, a, b, sum_templ, denom
@@ -176,7 +163,8 @@ struct rmd_seeds
 
   StagedMaps *maps;
   // busy-tile splitting of the staged kernel (depth_filter_staged.cu)
-  int n_tiles, cta_slots;
+  int n_tiles, cta_slots[2];    // resident CTAs of the staged kernel at 2 / 3 CTAs per SM
+  int ctas_per_sm;             // RMD_OPT_TUNE_CTAS_PER_SM: 0 automatic, 2, 3
   unsigned long long *tile_keys;
   unsigned int *tile_arrivals;
   unsigned int *heavy_list[3], *light_list[3], *sparse_list[3];  // work lists of frame f in [f % 3] (written during frame f - 1)
@@ -220,10 +208,7 @@ struct rmd_seeds
 namespace
 {
 
-int flush_pending(rmd_seeds *s);
-
-// Ring slot i: device image, pinned staging buffer, events (the first three at creation, the others when
-// RMD_OPT_HOST_FRAME_GROUP widens the ring).
+// Ring slot i: device image, pinned staging buffer, events.
 int ensure_slot(rmd_seeds *s, int i)
 {
   if(s->curr[i]) return 0;
@@ -247,7 +232,7 @@ int seeds_alloc(rmd_seeds *s)
   RMD_CUDA_TRY(cudaMalloc(&s->templ, sizeof(float2) * (size_t)s->templ_stride * h));
   RMD_CUDA_TRY(cudaMallocPitch(&s->conv, &s->conv_pitch, sizeof(int) * (size_t)w, h));
   RMD_CUDA_TRY(cudaMallocPitch(&s->ref, &s->ref_pitch, sizeof(float) * (size_t)w, h));
-  for(int i = 0; i < 3; ++i)
+  for(int i = 0; i < kSlots; ++i)
   {
     const int rc = ensure_slot(s, i);
     if(rc) return rc;
@@ -259,13 +244,16 @@ int seeds_alloc(rmd_seeds *s)
   {
     s->n_tiles = ((w + staged::TILE_W - 1) / staged::TILE_W) * ((h + staged::TILE_H - 1) / staged::TILE_H);
     // resident CTAs of the staged kernel = its persistent grid (SMs x occupancy: 3 per SM for 5x5, 2 for 7x7)
-    s->cta_slots = staged_cta_slots(s->patch);
-    if(s->cta_slots <= 0)
+    for(int mb = 2; mb <= 3; ++mb)
     {
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-      s->cta_slots = sms * (s->patch <= 5 ? 3 : 2);
-      cudaGetLastError();
+      s->cta_slots[mb - 2] = staged_cta_slots(s->patch, mb);
+      if(s->cta_slots[mb - 2] <= 0)
+      {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        s->cta_slots[mb - 2] = sms * (s->patch <= 5 ? mb : 2);
+        cudaGetLastError();
+      }
     }
     RMD_CUDA_TRY(cudaMalloc(&s->tile_keys, sizeof(unsigned long long) * (size_t)s->n_tiles * staged::NPIX));
     RMD_CUDA_TRY(cudaMalloc(&s->tile_arrivals, sizeof(unsigned int) * (size_t)s->n_tiles));
@@ -411,6 +399,15 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   return 0;
 }
 
+// Resident CTAs per SM of the 5x5 staged kernel for the next launch (RMD_OPT_TUNE_CTAS_PER_SM).  Automatic = the
+// 128-register build (2 per SM): no spills, room for the two-candidates-at-once NCC; measured equal to the
+// 80-register build (3 per SM) on search-heavy frames and faster on steady ones (profiles/r02_occupancy_ab.txt).
+int staged_ctas_per_sm(const rmd_seeds *s)
+{
+  if(s->patch > 5) return 2;
+  return s->ctas_per_sm == 3 ? 3 : 2;
+}
+
 // Host side of one update: pose chain, parameter block, TMA descriptors and -- when the keyframe's work
 // list is not valid (first frame, state upload, variant switch) -- its rebuild on the handle's stream.
 // Nothing is launched for the frame itself; `P` is ready for launch_depth_filter_*.
@@ -454,7 +451,8 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     const uint64_t f = s->frame_index;
     P.split_max = s->tune[0]; P.split_min_items = s->tune[1]; P.split_items_per_cta = s->tune[2];
     P.sparse_max_seeds = s->tune[3];
-    P.cta_slots = s->cta_slots;
+    P.ctas_per_sm = staged_ctas_per_sm(s);
+    P.cta_slots = s->cta_slots[P.ctas_per_sm - 2];
     P.tile_keys = s->tile_keys;
     P.tile_arrivals = s->tile_arrivals;
     P.n_tiles = s->n_tiles; P.tiles_x = s->tiles_x; P.helper_cap = staged::HELPER_CAP;
@@ -701,47 +699,6 @@ int enqueue_frames(rmd_seeds *s, const float *const *frames, size_t pitch_bytes,
   return 0;
 }
 
-// Launch the host frames whose kernel was deferred (RMD_OPT_HOST_FRAME_GROUP) and release their ring slots.
-int flush_pending(rmd_seeds *s)
-{
-  const int n = s->n_pending;
-  if(n == 0) return 0;
-  s->n_pending = 0;
-  DeviceGuard guard(s->device);
-  const float *frames[STAGED_BATCH_MAX];
-  for(int k = 0; k < n; ++k)
-    frames[k] = s->curr[s->pend_slot[k]];
-  const int rc = enqueue_frames(s, frames, s->curr_pitch, s->pend_pose, n);
-  if(rc) return rc;
-  for(int k = 0; k < n; ++k)
-    RMD_CUDA_TRY(cudaEventRecord(s->consumed[s->pend_slot[k]], s->stream));
-  return 0;
-}
-
-// A staged host frame: launch it now, or park it until the group is full.
-int submit_host_frame(rmd_seeds *s, int slot, const float *T_curr_world)
-{
-  if(s->host_group <= 1)
-  {
-    const int rc = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
-    if(rc) return rc;
-    RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
-    return 0;
-  }
-  {
-    // getDistFromRef (seed_matrix.cu:124-125) answers for this frame straight away
-    const Pose T_curr_ref = pose_compose(pose_from(T_curr_world), s->T_world_ref);
-    const float tx = T_curr_ref.m[3], ty = T_curr_ref.m[7], tz = T_curr_ref.m[11];
-    s->dist_from_ref = sqrtf(tx * tx + ty * ty + tz * tz);
-  }
-  s->pend_slot[s->n_pending] = slot;
-  memcpy(s->pend_pose + 12 * s->n_pending, T_curr_world, 12 * sizeof(float));
-  s->n_pending += 1;
-  if(s->n_pending >= s->host_group)
-    return flush_pending(s);
-  return 0;
-}
-
 // rmd::Depthmap::inputImage (src/depthmap.cpp:95-106) for a frame already on the
 // device: remap through the undistortion maps if the camera has them, then
 // 8U -> 32F * (1/255), in one kernel on the compute stream.
@@ -771,12 +728,8 @@ bool is_page_locked(const void *p)
 // compute stream wait for it.  Returns the slot.
 int stage_host_frame(rmd_seeds *s, const void *host_img, size_t elem_size, int *slot_out)
 {
-  const int slot = s->next_slot % s->ring_size;
-  s->next_slot = (slot + 1) % s->ring_size;
-  {
-    const int rc = ensure_slot(s, slot);
-    if(rc) return rc;
-  }
+  const int slot = s->next_slot;
+  s->next_slot = (slot + 1) % kSlots;
   const size_t row_bytes = elem_size * (size_t)s->width;
   // RMD_OPT_PINNED_INPUT: the caller's buffer is page-locked and stays untouched until the next sync,
   // so the DMA reads it in place (no staging copy, no wait for the pinned ring slot)
@@ -908,9 +861,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT; s->tune[6] = 1;
   s->tune[7] = staged::WARP_TILE_MAX_SEEDS;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
-  s->chain_frames = STAGED_BATCH_MAX;
-  s->ring_size = 3;
-  s->host_group = 1;
+  s->chain_frames = 1;   // chaining is opt-in: with the 128-register kernel it no longer pays (profiles/r02_occupancy_ab.txt)
   s->seed_mode_pct = 0;   // off by default: measured slower than the tile organisation on the bench workloads
   const int rc = seeds_alloc(s);
   if(rc)
@@ -935,7 +886,6 @@ int rmd_seeds_destroy(rmd_seeds_t *s)
 int rmd_seeds_set_stream(rmd_seeds_t *s, void *cuda_stream)
 {
   RMD_REQUIRE(s, "rmd_seeds_set_stream: null handle");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
   s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
@@ -945,7 +895,6 @@ int rmd_seeds_set_stream(rmd_seeds_t *s, void *cuda_stream)
 int rmd_seeds_get_stream(rmd_seeds_t *s, void **cuda_stream)
 {
   RMD_REQUIRE(s && cuda_stream, "rmd_seeds_get_stream: null");
-  RMD_FLUSH(s);
   *cuda_stream = (void*)s->stream;
   return 0;
 }
@@ -953,16 +902,10 @@ int rmd_seeds_get_stream(rmd_seeds_t *s, void **cuda_stream)
 int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
 {
   RMD_REQUIRE(s, "rmd_seeds_set_option: null handle");
-  RMD_FLUSH(s);
   switch(option)
   {
   case RMD_OPT_RECORD_MATCHES: s->record_matches = (value != 0); return 0;
   case RMD_OPT_PINNED_INPUT: s->pinned_input = (value != 0); return 0;
-  case RMD_OPT_HOST_FRAME_GROUP:
-    RMD_REQUIRE(value >= 1 && value <= STAGED_BATCH_MAX, "RMD_OPT_HOST_FRAME_GROUP: 1..8");
-    s->host_group = value;
-    s->ring_size = value > 1 ? value + 3 : 3;   // a slot is reused only after its group was launched
-    return 0;
   case RMD_OPT_CHAIN_FRAMES:
     RMD_REQUIRE(value >= 1 && value <= STAGED_BATCH_MAX, "RMD_OPT_CHAIN_FRAMES: 1..8");
     s->chain_frames = value;
@@ -1005,6 +948,10 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
     return 0;
+  case RMD_OPT_TUNE_CTAS_PER_SM:
+    RMD_REQUIRE(value == 0 || value == 2 || value == 3, "RMD_OPT_TUNE_CTAS_PER_SM: 0 (automatic), 2 or 3");
+    s->ctas_per_sm = value;
+    return 0;
   case RMD_OPT_TEX_FRAC_BITS:
     RMD_REQUIRE(value >= 0 && value <= 12, "RMD_OPT_TEX_FRAC_BITS: 0..12");
     s->tex_frac_bits = value;
@@ -1017,7 +964,6 @@ int rmd_seeds_set_reference(rmd_seeds_t *s, const float *host_img, const float *
                             float min_depth, float max_depth)
 {
   RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_set_reference: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t row = sizeof(float) * (size_t)s->width;
   // pageable source: returns once the data is staged, buffer reusable
@@ -1030,7 +976,6 @@ int rmd_seeds_set_reference_device(rmd_seeds_t *s, const float *dev_img, size_t 
                                    const float *T_curr_world, float min_depth, float max_depth)
 {
   RMD_REQUIRE(s && dev_img && T_curr_world, "rmd_seeds_set_reference_device: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t row = sizeof(float) * (size_t)s->width;
   RMD_REQUIRE(pitch_bytes >= row, "rmd_seeds_set_reference_device: pitch smaller than a row");
@@ -1043,7 +988,6 @@ int rmd_seeds_set_reference_u8(rmd_seeds_t *s, const uint8_t *host_img, const fl
                                float min_depth, float max_depth)
 {
   RMD_REQUIRE(s && host_img && T_curr_world, "rmd_seeds_set_reference_u8: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   // own scratch image: the ring slots belong to frames that may still be in flight
   if(!s->ref_u8)
@@ -1066,7 +1010,10 @@ int rmd_seeds_update(rmd_seeds_t *s, const float *host_img, const float *T_curr_
   int slot = 0;
   const int rc = stage_host_frame(s, host_img, sizeof(float), &slot);
   if(rc) return rc;
-  return submit_host_frame(s, slot, T_curr_world);
+  const int rc2 = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
+  if(rc2) return rc2;
+  RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
+  return 0;
 }
 
 int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_curr_world)
@@ -1080,7 +1027,10 @@ int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img, const float *T_
   int slot = 0;
   const int rc = stage_host_frame(s, host_img, sizeof(uint8_t), &slot);
   if(rc) return rc;
-  return submit_host_frame(s, slot, T_curr_world);
+  const int rc2 = enqueue_update(s, s->curr[slot], s->curr_pitch, T_curr_world);
+  if(rc2) return rc2;
+  RMD_CUDA_TRY(cudaEventRecord(s->consumed[slot], s->stream));
+  return 0;
 }
 
 namespace
@@ -1104,8 +1054,6 @@ int update_many(rmd_seeds_t *const *handles, int n, const void *host_img, size_t
   ProfScope prof(5);
   if(g_prof_on) g_prof[6] += 1.0;
   DeviceGuard guard(h0->device);
-  for(int i = 0; i < n; ++i)
-    RMD_FLUSH(handles[i]);
   for(int i = 0; i < n; ++i)
     if(!handles[i]->fan_ev)
       RMD_CUDA_TRY(cudaEventCreateWithFlags(&handles[i]->fan_ev, cudaEventDisableTiming));
@@ -1326,7 +1274,6 @@ int rmd_seeds_point_cloud(rmd_seeds_t *s, const float *dev_depth, size_t depth_p
                           float *host_xyzi, size_t capacity_points, size_t *count)
 {
   RMD_REQUIRE(s && count && (host_xyzi || capacity_points == 0), "rmd_seeds_point_cloud: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   if(!s->pc_points)
     RMD_CUDA_TRY(cudaMalloc(&s->pc_points, sizeof(float4) * (size_t)s->width * s->height));
@@ -1342,7 +1289,6 @@ int rmd_seeds_point_cloud_device(rmd_seeds_t *s, const float *dev_depth, size_t 
                                  float *dev_xyzi, size_t capacity_points, size_t *count)
 {
   RMD_REQUIRE(s && count && (dev_xyzi || capacity_points == 0), "rmd_seeds_point_cloud_device: null argument");
-  RMD_FLUSH(s);
   RMD_REQUIRE(((uintptr_t)dev_xyzi % 16) == 0, "rmd_seeds_point_cloud_device: output must be 16-byte aligned");
   DeviceGuard guard(s->device);
   return point_cloud_run(s, dev_depth, depth_pitch_bytes, reinterpret_cast<float4*>(dev_xyzi), capacity_points, count);
@@ -1352,7 +1298,6 @@ int rmd_seeds_update_device(rmd_seeds_t *s, const float *dev_img, size_t pitch_b
                             const float *T_curr_world)
 {
   RMD_REQUIRE(s && dev_img && T_curr_world, "rmd_seeds_update_device: null argument");
-  RMD_FLUSH(s);
   RMD_REQUIRE(pitch_bytes >= sizeof(float) * (size_t)s->width && pitch_bytes % 16 == 0 &&
               ((uintptr_t)dev_img % 16) == 0,
               "rmd_seeds_update_device: image must be 16-byte aligned with a pitch multiple of 16");
@@ -1373,7 +1318,6 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
   if(!s->has_reference)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_update_device_batch: set_reference has not been called");
   DeviceGuard guard(s->device);
-  RMD_FLUSH(s);
   const char *base = reinterpret_cast<const char*>(dev_frames);
   for(int i = 0; i < n_frames; i += SEED_FRAMES_MAX)
   {
@@ -1390,7 +1334,6 @@ int rmd_seeds_update_device_batch(rmd_seeds_t *s, const float *dev_frames, size_
 int rmd_seeds_sync(rmd_seeds_t *s)
 {
   RMD_REQUIRE(s, "rmd_seeds_sync: null handle");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   RMD_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
   RMD_CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1404,7 +1347,6 @@ int rmd_seeds_sync(rmd_seeds_t *s)
 int rmd_seeds_download(rmd_seeds_t *s, int field, void *host_dst)
 {
   RMD_REQUIRE(s && host_dst, "rmd_seeds_download: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t w = s->width, h = s->height;
   if(is_seed_field(field) || is_templ_field(field))
@@ -1451,7 +1393,6 @@ int rmd_seeds_download(rmd_seeds_t *s, int field, void *host_dst)
 int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
 {
   RMD_REQUIRE(s && host_src, "rmd_seeds_upload_state: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   {
     const int rc = wait_external(s);
@@ -1488,7 +1429,6 @@ int rmd_seeds_upload_state(rmd_seeds_t *s, int field, const void *host_src)
 int rmd_seeds_device_ptr(rmd_seeds_t *s, int field, void **dev_ptr, size_t *pitch_bytes)
 {
   RMD_REQUIRE(s && dev_ptr && pitch_bytes, "rmd_seeds_device_ptr: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   if(field == RMD_FIELD_CONVERGENCE)
   {
@@ -1530,7 +1470,6 @@ int rmd_seeds_device_ptr(rmd_seeds_t *s, int field, void **dev_ptr, size_t *pitc
 int rmd_seeds_copy_field_to_device(rmd_seeds_t *s, int field, void *dev_dst, size_t dst_pitch_bytes)
 {
   RMD_REQUIRE(s && dev_dst, "rmd_seeds_copy_field_to_device: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   const size_t w = s->width, h = s->height;
   if(is_seed_field(field) || is_templ_field(field))
@@ -1552,7 +1491,6 @@ int rmd_seeds_copy_field_to_device(rmd_seeds_t *s, int field, void *dev_dst, siz
 int rmd_seeds_converged_count(rmd_seeds_t *s, size_t *count)
 {
   RMD_REQUIRE(s && count, "rmd_seeds_converged_count: null argument");
-  RMD_FLUSH(s);
   DeviceGuard guard(s->device);
   if(s->mode == 1)
   {
@@ -1592,7 +1530,6 @@ int rmd_seeds_size(rmd_seeds_t *s, int *width, int *height, int *patch_side)
 int rmd_seeds_launch_count(rmd_seeds_t *s, uint64_t *fused, uint64_t *total)
 {
   RMD_REQUIRE(s, "rmd_seeds_launch_count: null handle");
-  RMD_FLUSH(s);
   if(fused) *fused = s->n_fused;
   if(total) *total = s->n_total;
   return 0;
@@ -1601,7 +1538,6 @@ int rmd_seeds_launch_count(rmd_seeds_t *s, uint64_t *fused, uint64_t *total)
 int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on)
 {
   RMD_REQUIRE(s, "rmd_seeds_enable_kernel_timing: null handle");
-  RMD_FLUSH(s);
   s->timing = (on != 0);
   s->t_valid = false;
   return 0;
@@ -1610,7 +1546,6 @@ int rmd_seeds_enable_kernel_timing(rmd_seeds_t *s, int on)
 int rmd_seeds_last_kernel_ms(rmd_seeds_t *s, float *ms)
 {
   RMD_REQUIRE(s && ms, "rmd_seeds_last_kernel_ms: null argument");
-  RMD_FLUSH(s);
   if(!s->t_valid)
     return fail(RMD_ERR_NOT_INITIALISED, "rmd_seeds_last_kernel_ms: timing not enabled / no kernel yet");
   DeviceGuard guard(s->device);
@@ -1801,7 +1736,6 @@ int rmd_denoiser_run(rmd_denoiser_t *d, const float *mu, size_t mu_pitch, const 
 
 static int run_seeds_common(rmd_denoiser_t *d, rmd_seeds_t *s, float lambda, int iterations, int *buf)
 {
-  RMD_FLUSH(s);
   if(d->large_sigma_sq < 0.0f)
     return fail(RMD_ERR_NOT_INITIALISED,
                 "rmd_denoiser_run_seeds: set_large_sigma_sq must be called before this function");

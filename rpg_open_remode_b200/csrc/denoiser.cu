@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include "denoiser.cuh"
+#include "packed_f32x2.cuh"
 
 namespace rmdb
 {
@@ -54,47 +55,6 @@ static_assert(TW + 2 * T_IT == EW && TH + 2 * T_IT == EH, "halo = iterations per
 __device__ __forceinline__ unsigned int smem_addr(const void *p)
 {
   return (unsigned int)__cvta_generic_to_shared(p);
-}
-
-// ---- packed fp32 pairs (Blackwell f32x2 pipe); a pair lives in one 64-bit register
-typedef unsigned long long f2;
-
-__device__ __forceinline__ f2 pack(const float lo, const float hi)
-{
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ f2 pack(const float2 v) { return pack(v.x, v.y); }
-__device__ __forceinline__ float2 unpack(const f2 v)
-{
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-__device__ __forceinline__ f2 f2_add(const f2 a, const f2 b)
-{
-  f2 r;
-  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2 f2_sub(const f2 a, const f2 b)
-{
-  f2 r;
-  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2 f2_mul(const f2 a, const f2 b)
-{
-  f2 r;
-  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f2 f2_fma(const f2 a, const f2 b, const f2 c)
-{
-  f2 r;
-  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
 }
 
 __device__ __forceinline__ float2 lds2(const float *p)

@@ -38,7 +38,7 @@ struct StagedMaps;
 cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const StagedMaps *const *maps, int n, int chain,
                                        unsigned int *cursor, int patch_side, cudaStream_t stream);
 // Resident CTAs of the staged kernel on the current device (SMs x occupancy), 0 on error.
-int staged_cta_slots(int patch_side);
+int staged_cta_slots(int patch_side, int ctas_per_sm);
 
 // Seed-major variant for the steady state of a keyframe (depth_filter_seeds.cu): the seeds that are still
 // updated are kept as a compact list; one launch walks every listed seed through up to SEED_FRAMES_MAX

@@ -11,6 +11,7 @@
 #include <math_constants.h>
 
 #include "rmd_common.cuh"
+#include "packed_f32x2.cuh"
 
 namespace rmdb
 {
@@ -284,6 +285,57 @@ __device__ __forceinline__ float ncc_score(
   const float numerator = __fmaf_rn(sum_img_templ, area, -__fmul_rn(sum_img, sum_templ));
   const float spread = __fmaf_rn(sum_img_sq, area, -__fmul_rn(sum_img, sum_img));
   return __fmul_rn(numerator, rsqrtf(__fmaf_rn(const_templ_denom, spread, FLT_MIN)));
+}
+
+// Two candidates at once: lane 0 of every packed register belongs to candidate A, lane 1 to candidate B.
+// The texels of the two blocks are loaded into adjacent registers, the separable filter and the sums of
+// squares run as f32x2 operations (one issue slot for both candidates), the template products stay scalar
+// (the template is shared by the two lanes).  Each lane performs exactly ncc_score's operations in
+// ncc_score's order, so the two results are bit for bit those of two ncc_score calls.
+template<int PS, typename Taps>
+__device__ __forceinline__ float2 ncc_score_pair(
+    const Taps &taps_a, const TapFrame &ta, const Taps &taps_b, const TapFrame &tb, const float (&templ)[PS * PS],
+    const float sum_templ, const float const_templ_denom)
+{
+  const f2 wx0 = pack(ta.wx0, tb.wx0), wx1 = pack(ta.wx1, tb.wx1);
+  const f2 wy0 = pack(ta.wy0, tb.wy0), wy1 = pack(ta.wy1, tb.wy1);
+  f2 sum_img = pack(0.0f, 0.0f), sum_img_sq = pack(0.0f, 0.0f);
+  float sum_it_a = 0.0f, sum_it_b = 0.0f;
+  f2 upper[PS];
+#pragma unroll
+  for(int j = 0; j <= PS; ++j)
+  {
+    f2 v[PS + 1];
+#pragma unroll
+    for(int i = 0; i <= PS; ++i) v[i] = pack(taps_a.at(j, i), taps_b.at(j, i));
+    f2 lower[PS];
+#pragma unroll
+    for(int i = 0; i < PS; ++i) lower[i] = f2_fma(v[i], wx0, f2_mul(v[i + 1], wx1));
+    if(j > 0)
+    {
+#pragma unroll
+      for(int i = 0; i < PS; ++i)
+      {
+        const f2 img = f2_fma(upper[i], wy0, f2_mul(lower[i], wy1));
+        const float2 im = unpack(img);
+        const float tv = templ[(j - 1) * PS + i];
+        sum_img = f2_add(sum_img, img);
+        sum_img_sq = f2_fma(img, img, sum_img_sq);
+        sum_it_a = __fmaf_rn(im.x, tv, sum_it_a);
+        sum_it_b = __fmaf_rn(im.y, tv, sum_it_b);
+      }
+    }
+#pragma unroll
+    for(int i = 0; i < PS; ++i) upper[i] = lower[i];
+  }
+  const float area = (float)(PS * PS);
+  const float2 si = unpack(sum_img), sq = unpack(sum_img_sq);
+  const float num_a = __fmaf_rn(sum_it_a, area, -__fmul_rn(si.x, sum_templ));
+  const float num_b = __fmaf_rn(sum_it_b, area, -__fmul_rn(si.y, sum_templ));
+  const float spread_a = __fmaf_rn(sq.x, area, -__fmul_rn(si.x, si.x));
+  const float spread_b = __fmaf_rn(sq.y, area, -__fmul_rn(si.y, si.y));
+  return make_float2(__fmul_rn(num_a, rsqrtf(__fmaf_rn(const_templ_denom, spread_a, FLT_MIN))),
+                     __fmul_rn(num_b, rsqrtf(__fmaf_rn(const_templ_denom, spread_b, FLT_MIN))));
 }
 
 // Texel block of a candidate read straight from a pitched global image

@@ -612,39 +612,77 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
 #if RMD_DEBUG_COUNTERS
       const long long dbg_t1 = clock64();
 #endif
+      // Two candidates per pass: when both lie in the strip their texel blocks are filtered together with
+      // packed f32x2 operations (ncc_score_pair); otherwise each goes the scalar way (strip or global taps).
+      // l advances by the reference's own float accumulation either way.
+      static_assert(CHUNK % 2 == 0, "candidates are taken two at a time");
 #pragma unroll 1
-      for(int i = 0; i < CHUNK; ++i, l += RMD_EPIPOLAR_STEP)
+      for(int i = 0; i < CHUNK; i += 2)
       {
-        if(!(l <= R.half_len)) break;
-        const float2 px = candidate_px(R.mean_x, R.mean_y, R.dir_x, R.dir_y, l);
-        if(candidate_rejected<PS>(px, P.width, P.height))
-          continue;
-        const TapFrame frame = tap_frame<PS>(px, P.tex_quant);
-        const bool in_strip = (frame.i0 >= strip_ox) && (frame.i0 + PS < strip_ox + strip_w) &&
-                              (frame.j0 >= strip_oy) && (frame.j0 + PS < strip_oy + strip_rows);
-        float ncc;
+        const float l0 = l;
+        l += RMD_EPIPOLAR_STEP;
+        const float l1 = l;
+        l += RMD_EPIPOLAR_STEP;
+        if(!(l0 <= R.half_len)) break;
+        const float2 px0 = candidate_px(R.mean_x, R.mean_y, R.dir_x, R.dir_y, l0);
+        const float2 px1 = candidate_px(R.mean_x, R.mean_y, R.dir_x, R.dir_y, l1);
+        const bool use0 = !candidate_rejected<PS>(px0, P.width, P.height);
+        const bool use1 = (l1 <= R.half_len) && !candidate_rejected<PS>(px1, P.width, P.height);
+        const TapFrame frame0 = tap_frame<PS>(px0, P.tex_quant);
+        const TapFrame frame1 = tap_frame<PS>(px1, P.tex_quant);
+        const bool in0 = (frame0.i0 >= strip_ox) && (frame0.i0 + PS < strip_ox + strip_w) &&
+                         (frame0.j0 >= strip_oy) && (frame0.j0 + PS < strip_oy + strip_rows);
+        const bool in1 = (frame1.i0 >= strip_ox) && (frame1.i0 + PS < strip_ox + strip_w) &&
+                         (frame1.j0 >= strip_oy) && (frame1.j0 + PS < strip_oy + strip_rows);
+        float ncc0 = -2.0f, ncc1 = -2.0f;     // below every score: a skipped candidate never wins
 #if RMD_DEBUG_COUNTERS
         if(P.timeline)
         {
-          atomicAdd(&S.dbg[in_strip ? 0 : 1], 1);                  // candidates (lanes)
+          if(use0) atomicAdd(&S.dbg[in0 ? 0 : 1], 1);              // candidates (lanes)
+          if(use1) atomicAdd(&S.dbg[in1 ? 0 : 1], 1);
           const unsigned int am = __activemask();
-          if(lane == __ffs(am) - 1) atomicAdd(&S.dbg[in_strip ? 2 : 3], 1);  // warp-level executions of each path
+          if(lane == __ffs(am) - 1) atomicAdd(&S.dbg[(in0 && in1) ? 2 : 3], 1);  // warp-level executions of each path
         }
 #endif
-        if(in_strip)
+        if(use0 && use1 && in0 && in1)
         {
-          const StripTaps taps(S.strip, strip_w, strip_ox, strip_oy, frame);
-          ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+          const StripTaps taps0(S.strip, strip_w, strip_ox, strip_oy, frame0);
+          const StripTaps taps1(S.strip, strip_w, strip_ox, strip_oy, frame1);
+          const float2 both = ncc_score_pair<PS>(taps0, frame0, taps1, frame1, templ, R.sum_templ, R.denom);
+          ncc0 = both.x;
+          ncc1 = both.y;
         }
         else
         {
-          const GlobalTaps taps(P.curr, P.curr_stride, frame);
-          ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+#pragma unroll 1
+          for(int h = 0; h < 2; ++h)
+          {
+            if(!(h == 0 ? use0 : use1))
+              continue;
+            const TapFrame frame = (h == 0) ? frame0 : frame1;
+            float ncc;
+            if(h == 0 ? in0 : in1)
+            {
+              const StripTaps taps(S.strip, strip_w, strip_ox, strip_oy, frame);
+              ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+            }
+            else
+            {
+              const GlobalTaps taps(P.curr, P.curr_stride, frame);
+              ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
+            }
+            if(h == 0) ncc0 = ncc; else ncc1 = ncc;
+          }
         }
-        if(ncc > best_ncc)
+        if(ncc0 > best_ncc)
         {
-          best_ncc = ncc;
+          best_ncc = ncc0;
           best_idx = first + i;
+        }
+        if(ncc1 > best_ncc)
+        {
+          best_ncc = ncc1;
+          best_idx = first + i + 1;
         }
       }
       if(best_ncc > -1.0f)
@@ -942,14 +980,12 @@ __device__ __forceinline__ void process_warp_tile(const FilterParams &P, StagedS
 // with nothing left to update, ever, are not listed.  K > 1: the lists of up to K keyframes (independent
 // reference views updated by the same incoming frame) are concatenated -- all heavy lists, then all light
 // lists -- so the dependent chains of different keyframes interleave from the first cycle.
-// CTAs per SM the register budget is sized for (5x5 patch: 3 x 256 threads x 80 registers; tools/build_variant_lib.sh
-// builds the 2-CTA / 128-register alternative for the A/B in profiles/r02_tune_probe.txt)
-#ifndef RMD_STAGED_P5_MIN_BLOCKS
-#define RMD_STAGED_P5_MIN_BLOCKS 3
-#endif
-
-template<int PS, int K>
-__global__ void __launch_bounds__(NTHREADS, (PS <= 5 ? RMD_STAGED_P5_MIN_BLOCKS : 2)) depth_filter_staged_kernel(
+// MB = CTAs per SM the register budget is sized for.  The 5x5 kernel exists as 3 x 256 threads x 80 registers
+// (24 warps per SM: more issue slots covered when every seed searches its full range) and as 2 x 256 x 128
+// (no spills, shorter dependent chains: faster when a frame is the critical path of a few CTAs); the host picks
+// per launch (RMD_OPT_TUNE_CTAS_PER_SM, c_api.cu).  The 7x7 kernel needs 128 registers.
+template<int PS, int K, int MB>
+__global__ void __launch_bounds__(NTHREADS, MB) depth_filter_staged_kernel(
     const __grid_constant__ StagedBatch<K> B)
 {
   extern __shared__ unsigned char smem_raw[];
@@ -1178,7 +1214,7 @@ int StagedMaps::encode(const FilterParams &P, int patch_side)
 namespace
 {
 
-template<int PS, int K>
+template<int PS, int K, int MB>
 struct StagedLaunch
 {
   static size_t smem_bytes() { return sizeof(StagedSmem<PS>) + 128; }  // slack for the manual 128-byte alignment
@@ -1193,11 +1229,11 @@ struct StagedLaunch
       return 0;
     if(cached[device] == 0)
     {
-      if(cudaFuncSetAttribute(depth_filter_staged_kernel<PS, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      if(cudaFuncSetAttribute(depth_filter_staged_kernel<PS, K, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)smem_bytes()) != cudaSuccess)
         return 0;
       int per_sm = 0, sms = 0;
-      if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_filter_staged_kernel<PS, K>, NTHREADS,
+      if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_filter_staged_kernel<PS, K, MB>, NTHREADS,
                                                        smem_bytes()) != cudaSuccess ||
          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
         return 0;
@@ -1244,7 +1280,7 @@ struct StagedLaunch
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = P[0]->pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, depth_filter_staged_kernel<PS, K>, B);
+    return cudaLaunchKernelEx(&cfg, depth_filter_staged_kernel<PS, K, MB>, B);
   }
 };
 
@@ -1258,22 +1294,25 @@ cudaError_t launch_depth_filter_staged(const FilterParams *const *P, const Stage
   // RMD_FORCE_BATCH_KERNEL=1 (test hook): single keyframes also go through the batched instantiation
   static const bool force_batch = (getenv("RMD_FORCE_BATCH_KERNEL") != NULL);
   const bool single = (n == 1) && !force_batch && !chain;
+  if(patch_side == 5 && P[0]->ctas_per_sm == 2)
+    return single ? StagedLaunch<5, 1, 2>::launch(P, maps, n, 0, cursor, stream)
+                  : StagedLaunch<5, STAGED_BATCH_MAX, 2>::launch(P, maps, n, chain, cursor, stream);
   if(patch_side == 5)
-    return single ? StagedLaunch<5, 1>::launch(P, maps, n, 0, cursor, stream)
-                  : StagedLaunch<5, STAGED_BATCH_MAX>::launch(P, maps, n, chain, cursor, stream);
+    return single ? StagedLaunch<5, 1, 3>::launch(P, maps, n, 0, cursor, stream)
+                  : StagedLaunch<5, STAGED_BATCH_MAX, 3>::launch(P, maps, n, chain, cursor, stream);
   if(patch_side == 7)
-    return single ? StagedLaunch<7, 1>::launch(P, maps, n, 0, cursor, stream)
-                  : StagedLaunch<7, STAGED_BATCH_MAX>::launch(P, maps, n, chain, cursor, stream);
+    return single ? StagedLaunch<7, 1, 2>::launch(P, maps, n, 0, cursor, stream)
+                  : StagedLaunch<7, STAGED_BATCH_MAX, 2>::launch(P, maps, n, chain, cursor, stream);
   return cudaErrorInvalidValue;
 }
 
-int staged_cta_slots(int patch_side)
+int staged_cta_slots(int patch_side, int ctas_per_sm)
 {
   int device = 0;
   if(cudaGetDevice(&device) != cudaSuccess)
     return 0;
-  if(patch_side == 5) return StagedLaunch<5, 1>::slots(device);
-  if(patch_side == 7) return StagedLaunch<7, 1>::slots(device);
+  if(patch_side == 5) return ctas_per_sm == 2 ? StagedLaunch<5, 1, 2>::slots(device) : StagedLaunch<5, 1, 3>::slots(device);
+  if(patch_side == 7) return StagedLaunch<7, 1, 2>::slots(device);
   return 0;
 }
 

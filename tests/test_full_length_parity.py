@@ -108,13 +108,14 @@ def test_device_resident_path_equals_host_path(patch, size):
     want = _snap(host)
 
     batch = rmd.SeedMatrix(W, H, cam, patch_side=patch)
+    batch.setOption(rmd.OPT_CHAIN_FRAMES, 8)
     batch.setReferenceImageDevice(dense[0].data_ptr(), W * 4, poses[0], dmin, dmax)
     batch.updateDeviceBatch(dense[1].data_ptr(), W * H * 4, W * 4, poses[1:])
     single = rmd.SeedMatrix(W, H, cam, patch_side=patch)
     single.setReferenceImageDevice(dense[0].data_ptr(), W * 4, poses[0], dmin, dmax)
     for k in range(1, N):
         single.updateDevice(dense[k].data_ptr(), W * 4, poses[k])
-    # the same with 3 frames and with 1 frame per chained launch (RMD_OPT_CHAIN_FRAMES; default 8)
+    # the same with 3 frames and with 1 frame (the default) per launch (RMD_OPT_CHAIN_FRAMES)
     others = []
     for frames_per_launch in (3, 1):
         g = rmd.SeedMatrix(W, H, cam, patch_side=patch)

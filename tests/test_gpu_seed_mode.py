@@ -72,6 +72,7 @@ def test_seed_mode_device_batches_and_state_upload():
     Wn = _snap(want)
     # device batches: chained tile launches until the statistics arrive, then seed-major launches of up to 16 frames
     g = _new(seq, f0, dmin, dmax, pct=100)
+    g.setOption(rmd.OPT_CHAIN_FRAMES, 8)
     g.updateDeviceBatch(dense[1].data_ptr(), W * H * 4, W * 4, poses[1:7])
     g.updateDeviceBatch(dense[7].data_ptr(), W * H * 4, W * 4, poses[7:50])
     g.updateDeviceBatch(dense[50].data_ptr(), W * H * 4, W * 4, poses[50:])

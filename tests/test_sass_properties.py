@@ -1,7 +1,8 @@
 """What the shipped library is made of, checked on the CPU box with cuobjdump: every cubin is sm_100a, and the
 fused staged kernel really contains the Blackwell mechanisms DESIGN.md 4.1 describes -- TMA tensor loads
 (UTMALDG.2D) completing on an mbarrier (SYNCS ... TRANS64), programmatic dependent launch (ACQBULK =
-griddepcontrol.wait), warp-level reductions (REDUX) -- with the register budget that gives 3 CTAs per SM."""
+griddepcontrol.wait), warp-level reductions (REDUX) -- in both register budgets of the 5x5 kernel: 80 registers (3 CTAs of
+256 threads per SM) and 128 registers without spills (2 CTAs per SM)."""
 import os
 import re
 import shutil
@@ -11,7 +12,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
-STAGED5 = "_ZN4rmdb26depth_filter_staged_kernelILi5ELi1EEEvNS_11StagedBatchIXT0_EEE"
+STAGED5 = "_ZN4rmdb26depth_filter_staged_kernelILi5ELi1ELi3EEEvNS_11StagedBatchIXT0_EEE"
+STAGED5_MB2 = "_ZN4rmdb26depth_filter_staged_kernelILi5ELi1ELi2EEEvNS_11StagedBatchIXT0_EEE"
 
 pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump not installed")
 
@@ -46,3 +48,8 @@ def test_staged_kernel_resources(lib):
     assert m, out[-2000:]
     regs = int(re.search(r"REG:(\d+)", m.group(1)).group(1))
     assert regs <= 80, f"{regs} registers: 3 CTAs of 256 threads per SM need <= 80"
+    m2 = re.search(r"Function " + STAGED5_MB2 + r":\s*\n\s*(.*)", out)
+    assert m2, out[-2000:]
+    regs2 = int(re.search(r"REG:(\d+)", m2.group(1)).group(1))
+    stack2 = int(re.search(r"STACK:(\d+)", m2.group(1)).group(1))
+    assert regs2 <= 128 and stack2 == 0, f"{regs2} registers, {stack2} bytes of stack: the 2-CTA build must not spill"

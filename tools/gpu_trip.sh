@@ -19,20 +19,7 @@ for stage in "$@"; do
     smoke)      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log ;;
     bench)      timeout 900 python bench.py > $OUT/bench_c2.json 2> $OUT/bench_c2.err; tail -c 600 $OUT/bench_c2.json ;;
     bench_seedpct) for pct in 0 15 25 40; do timeout 600 python bench.py --seed-mode-pct $pct --no-cpu-baseline --steps 10 > $OUT/bench_c2_seed$pct.json 2> $OUT/bench_c2_seed$pct.err; python -c "import json; d=json.loads(open('gpurun_out/bench_c2_seed$pct.json').read()); print('seed pct $pct: value', round(d['value']), 'ms', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), round(d['e2e']['ms_per_step'],2), 'fused launches/step', d['gpu_launches_fused']/10)"; done ;;
-    variant_mb2) echo 'default library (3 CTAs/SM, 80 registers):'; timeout 300 python tools/tune_probe.py 16,512,384,16,32,100,1,8,8,0 16,512,384,16,32,100,1,8,1,0 2>&1 | tail -n 2
-                echo 'variant mb2 (2 CTAs/SM, 128 registers):'; RMD_B200_LIB=$PWD/rpg_open_remode_b200/build/librmd_b200_mb2.so timeout 300 python tools/tune_probe.py 16,512,384,16,32,100,1,8,8,0 16,512,384,16,32,100,1,8,1,0 2>&1 | tail -n 2 ;;
-    grid_probe) for lib in librmd_b200.so build/librmd_b200_mb2.so; do echo "library $lib:"
-                  RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 300 python tools/tune_probe.py 16,512,384,16,32,100,1,8,8,0,0 16,512,384,16,32,100,1,8,8,0,296 16,512,384,16,32,100,1,8,8,0,222 16,512,384,16,32,100,1,8,8,0,148 16,512,384,16,32,100,1,8,1,0,296 16,512,384,16,32,100,1,8,1,0,222 16,512,384,16,32,100,1,8,1,0,148 2>&1 | tail -n 7; done ;;
-    group_probe) for g in 1 2 4 8; do timeout 600 python bench.py --host-group $g --no-cpu-baseline > $OUT/bench_c2_group$g.json 2> $OUT/bench_c2_group$g.err
-                  python -c "import json; r=json.loads(open('$OUT/bench_c2_group$g.json').read()); print('host group $g: value', round(r['value']), 'ms', r['ms_per_step'], 'e2e', round(r['e2e']['value']), r['e2e'].get('ms_per_step'))"; done ;;
-    ab_720p)    for lib in librmd_b200.so build/librmd_b200_mb2.so; do echo "library $lib, 1280x720 x 300 frames:"
-                  RMD_PROBE_SIZE=1280,720,300 RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 600 python tools/tune_probe.py 16,512,384,16,32,100,1,8,8,0 16,512,384,16,32,100,1,8,1,0 2>&1 | tail -n 2; done ;;
-    ab_mb2)     for lib in librmd_b200.so build/librmd_b200_mb2.so; do export RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib; echo "library $lib:"
-                  for g in 1 8; do timeout 600 python bench.py --host-group $g --no-cpu-baseline > $OUT/ab.json 2> $OUT/ab.err
-                    python -c "import json; r=json.loads(open('$OUT/ab.json').read()); print('  c2 host group $g: value', round(r['value']), 'ms', round(r['ms_per_step'],3), 'e2e', round(r['e2e']['value']), round(r['e2e'].get('ms_per_step',0),3))"; done
-                  timeout 600 python bench.py --config c3 --steps 3 --host-group 8 --no-cpu-baseline > $OUT/ab.json 2> $OUT/ab.err
-                  python -c "import json; r=json.loads(open('$OUT/ab.json').read()); print('  c3: value', round(r['value']), 'ms', round(r['ms_per_step'],3), 'e2e', round(r['e2e']['value']), round(r['e2e'].get('ms_per_step',0),3))"
-                  timeout 600 python tools/multi_keyframe_probe.py 2>&1 | tail -n 5; done; unset RMD_B200_LIB ;;
+    occupancy_ab) for size in 640,480,200 1280,720,300; do echo "image, frames: $size"; RMD_PROBE_SIZE=$size timeout 600 python tools/tune_probe.py 2>&1 | tail -n 4; done ;;
     bench_c3)   timeout 900 python bench.py --config c3 > $OUT/bench_c3.json 2> $OUT/bench_c3.err ;;
     bench_c4)   timeout 900 python bench.py --config c4 > $OUT/bench_c4.json 2> $OUT/bench_c4.err ;;
     bench_c4_ab) timeout 900 python bench.py --config c4 --frames 120 --no-e2e --no-cpu-baseline --chain-frames 1 > $OUT/bench_c4_chain1.json 2> $OUT/bench_c4_chain1.err
