@@ -52,6 +52,12 @@
 #define RMD_DEBUG_COUNTERS 0
 #endif
 
+// Largest patch side whose candidates are scored two at a time with packed f32x2 operations (ncc_score_pair);
+// tools/build_variant_lib.sh builds the A/B alternatives.
+#ifndef RMD_STAGED_PAIR_MAX_PS
+#define RMD_STAGED_PAIR_MAX_PS 7
+#endif
+
 namespace rmdb
 {
 
@@ -616,6 +622,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       // packed f32x2 operations (ncc_score_pair); otherwise each goes the scalar way (strip or global taps).
       // l advances by the reference's own float accumulation either way.
       static_assert(CHUNK % 2 == 0, "candidates are taken two at a time");
+      constexpr bool kPair = (PS <= RMD_STAGED_PAIR_MAX_PS);
 #pragma unroll 1
       for(int i = 0; i < CHUNK; i += 2)
       {
@@ -644,7 +651,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
           if(lane == __ffs(am) - 1) atomicAdd(&S.dbg[(in0 && in1) ? 2 : 3], 1);  // warp-level executions of each path
         }
 #endif
-        if(use0 && use1 && in0 && in1)
+        if(kPair && use0 && use1 && in0 && in1)
         {
           const StripTaps taps0(S.strip, strip_w, strip_ox, strip_oy, frame0);
           const StripTaps taps1(S.strip, strip_w, strip_ox, strip_oy, frame1);

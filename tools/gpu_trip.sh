@@ -19,6 +19,9 @@ for stage in "$@"; do
     smoke)      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log ;;
     bench)      timeout 900 python bench.py > $OUT/bench_c2.json 2> $OUT/bench_c2.err; tail -c 600 $OUT/bench_c2.json ;;
     bench_seedpct) for pct in 0 15 25 40; do timeout 600 python bench.py --seed-mode-pct $pct --no-cpu-baseline --steps 10 > $OUT/bench_c2_seed$pct.json 2> $OUT/bench_c2_seed$pct.err; python -c "import json; d=json.loads(open('gpurun_out/bench_c2_seed$pct.json').read()); print('seed pct $pct: value', round(d['value']), 'ms', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), round(d['e2e']['ms_per_step'],2), 'fused launches/step', d['gpu_launches_fused']/10)"; done ;;
+    pair_ab)    for lib in librmd_b200.so build/librmd_b200_nopair.so; do echo "library $lib:"
+                  for cfg in 640,480,200,5 640,480,200,7 1280,720,300,5 1920,1080,120,7; do
+                    RMD_PROBE_SIZE=${cfg%,*} RMD_PROBE_PATCH=${cfg##*,} RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 600 python tools/tune_probe.py 16,512,384,16,32,100,1,8,1,0,0,2 2>&1 | tail -n 1 | sed "s/^.*ctas.sm 2/  $cfg/"; done; done ;;
     occupancy_ab) for size in 640,480,200 1280,720,300; do echo "image, frames: $size"; RMD_PROBE_SIZE=$size timeout 600 python tools/tune_probe.py 2>&1 | tail -n 4; done ;;
     bench_c3)   timeout 900 python bench.py --config c3 > $OUT/bench_c3.json 2> $OUT/bench_c3.err ;;
     bench_c4)   timeout 900 python bench.py --config c4 > $OUT/bench_c4.json 2> $OUT/bench_c4.err ;;
