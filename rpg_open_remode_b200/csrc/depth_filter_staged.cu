@@ -651,13 +651,17 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
           if(lane == __ffs(am) - 1) atomicAdd(&S.dbg[(in0 && in1) ? 2 : 3], 1);  // warp-level executions of each path
         }
 #endif
-        if(kPair && use0 && use1 && in0 && in1)
+        if(!use0 && !use1)
+          continue;
+        // both usable candidates in the strip (a lone one is paired with itself): packed; otherwise both from global memory
+        if(kPair && (in0 || !use0) && (in1 || !use1))
         {
-          const StripTaps taps0(S.strip, strip_w, strip_ox, strip_oy, frame0);
-          const StripTaps taps1(S.strip, strip_w, strip_ox, strip_oy, frame1);
-          const float2 both = ncc_score_pair<PS>(taps0, frame0, taps1, frame1, templ, R.sum_templ, R.denom);
-          ncc0 = both.x;
-          ncc1 = both.y;
+          const TapFrame fa = use0 ? frame0 : frame1, fb = use1 ? frame1 : frame0;
+          const StripTaps taps_a(S.strip, strip_w, strip_ox, strip_oy, fa);
+          const StripTaps taps_b(S.strip, strip_w, strip_ox, strip_oy, fb);
+          const float2 both = ncc_score_pair<PS>(taps_a, fa, taps_b, fb, templ, R.sum_templ, R.denom);
+          if(use0) ncc0 = both.x;
+          if(use1) ncc1 = both.y;
         }
         else
         {
@@ -668,7 +672,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
               continue;
             const TapFrame frame = (h == 0) ? frame0 : frame1;
             float ncc;
-            if(h == 0 ? in0 : in1)
+            if(!kPair && (h == 0 ? in0 : in1))
             {
               const StripTaps taps(S.strip, strip_w, strip_ox, strip_oy, frame);
               ncc = ncc_score<PS>(taps, frame, templ, R.sum_templ, R.denom);
