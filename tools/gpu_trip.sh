@@ -22,6 +22,14 @@ for stage in "$@"; do
     pair_ab)    for lib in librmd_b200.so build/librmd_b200_nopair.so; do echo "library $lib:"
                   for cfg in 640,480,200,5 640,480,200,7 1280,720,300,5 1920,1080,120,7; do
                     RMD_PROBE_SIZE=${cfg%,*} RMD_PROBE_PATCH=${cfg##*,} RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 600 python tools/tune_probe.py 16,512,384,16,32,100,1,8,1,0,0,2 2>&1 | tail -n 1 | sed "s/^.*ctas.sm 2/  $cfg/"; done; done ;;
+    knobs)      T=",1,8,1,0,0,2"; timeout 600 python tools/tune_probe.py 16,512,384,16,32,100$T 16,512,384,24,32,100$T 16,512,384,32,32,100$T 16,512,384,48,32,100$T 16,512,384,64,32,100$T \
+                  16,256,128,16,32,100$T 32,256,128,16,32,100$T 16,384,256,16,32,100$T 16,512,384,16,32,50$T 16,512,384,16,32,200$T 16,512,384,16,16,100$T 16,512,384,16,64,100$T 16,512,384,16,32,100$T 2>&1 | tail -n 13 | sed 's/min_items/mi/;s/per_cta/pc/;s/heavy_min/hm/;s/avg_pct/ap/;s/pdl 1 warp_tiles 8 chain 1 seed_pct 0 grid 0 ctas.sm 2//' ;;
+    knobs2)     T=",1,8,1,0,0,2"; timeout 600 python tools/tune_probe.py 16,512,384,16,32,100$T 16,512,384,16,64,100$T 16,512,384,16,96,100$T 16,512,384,16,128,100$T 16,512,384,16,192,100$T 16,512,384,16,256,100$T 16,512,384,16,512,100$T \
+                  16,512,384,16,64,50$T 16,512,384,16,128,50$T 16,512,384,16,64,70$T 16,384,256,16,64,100$T 16,384,256,16,128,70$T 16,512,384,16,32,100$T 2>&1 | tail -n 13 | sed 's/min_items/mi/;s/per_cta/pc/;s/heavy_min/hm/;s/avg_pct/ap/;s/pdl 1 warp_tiles 8 chain 1 seed_pct 0 grid 0 ctas.sm 2//' ;;
+    rolled_ab)  T=",1,8,1,0,0,2"; for lib in librmd_b200.so build/librmd_b200_rolled.so; do echo "library $lib:"
+                  RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 600 python tools/tune_probe.py 16,512,384,16,32,100$T 16,512,384,16,64,100$T 2>&1 | tail -n 2 | sed 's/^.*ctas.sm 2/  VGA/'
+                  RMD_PROBE_SIZE=1280,720,300 RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 600 python tools/tune_probe.py 16,512,384,16,32,100$T 16,512,384,16,64,100$T 2>&1 | tail -n 2 | sed 's/^.*ctas.sm 2/  720p/'; done ;;
+    ncu_warm)   timeout 900 ncu --cache-control none --clock-control none --section WarpStateStats --section SchedulerStats -k regex:depth_filter_staged -s 129 -c 1 $BENCH_NCU 2>&1 | grep -v "^==PROF==" | tail -n 60 > $OUT/ncu_p5_steady_warm.txt; cat $OUT/ncu_p5_steady_warm.txt ;;
     occupancy_ab) for size in 640,480,200 1280,720,300; do echo "image, frames: $size"; RMD_PROBE_SIZE=$size timeout 600 python tools/tune_probe.py 2>&1 | tail -n 4; done ;;
     bench_c3)   timeout 900 python bench.py --config c3 > $OUT/bench_c3.json 2> $OUT/bench_c3.err ;;
     bench_c4)   timeout 900 python bench.py --config c4 > $OUT/bench_c4.json 2> $OUT/bench_c4.err ;;

@@ -23,7 +23,11 @@ METRICS = [
     "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
     "sm__cycles_active.min", "sm__cycles_active.max", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-]
+    "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__issue_active.avg.per_cycle_active",
+] + ["smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % r for r in (
+    "wait", "short_scoreboard", "long_scoreboard", "barrier", "math_pipe_throttle", "mio_throttle", "no_instruction",
+    "branch_resolving", "dispatch_stall", "not_selected", "membar")]
 TO_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
