@@ -189,7 +189,7 @@ struct rmd_seeds
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  int tune[9];                 // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds, grid_ctas
+  int tune[11];                // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds, grid_ctas, (ctas_per_sm: own field), warp_tile_max_cands
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
   // lens undistortion of 8-bit frames (ingest.cuh); maps are null until init_undistortion_map
   short2 *undist_xy; uint16_t *undist_frac;
@@ -461,6 +461,7 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.light_cur = s->light_list[f % 3]; P.light_next = s->light_list[(f + 1) % 3];
     P.sparse_cur = s->sparse_list[f % 3]; P.sparse_next = s->sparse_list[(f + 1) % 3];
     P.warp_tile_max_seeds = s->tune[7];
+    P.warp_tile_max_cands = s->tune[10];
     P.grid_ctas = s->tune[8];
     P.counts_cur = s->work_counts + 8 * (f % 3);
     P.counts_next = s->work_counts + 8 * ((f + 1) % 3);
@@ -860,6 +861,7 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[2] = staged::SPLIT_ITEMS_PER_CTA; s->tune[3] = staged::SPARSE_MAX_SEEDS;
   s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT; s->tune[6] = 1;
   s->tune[7] = staged::WARP_TILE_MAX_SEEDS;
+  s->tune[10] = staged::WARP_TILE_MAX_CANDS;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
   s->chain_frames = 1;   // chaining is opt-in: with the 128-register kernel it no longer pays (profiles/r02_occupancy_ab.txt)
   s->seed_mode_pct = 0;   // off by default: measured slower than the tile organisation on the bench workloads
@@ -941,10 +943,10 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   }
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
   case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT: case RMD_OPT_TUNE_PDL:
-  case RMD_OPT_TUNE_WARP_TILE_SEEDS: case RMD_OPT_TUNE_GRID_CTAS:
+  case RMD_OPT_TUNE_WARP_TILE_SEEDS: case RMD_OPT_TUNE_GRID_CTAS: case RMD_OPT_TUNE_WARP_TILE_CANDS:
     RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL ||
                            option == RMD_OPT_TUNE_WARP_TILE_SEEDS || option == RMD_OPT_TUNE_GRID_CTAS) ? 0 : 1) && value <= 65535, "tuning value out of range");
-    RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= staged::WARP_TILE_MAX_SEEDS, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..8");
+    RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= 32, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..32");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
     return 0;

@@ -107,18 +107,13 @@ __device__ __forceinline__ int count_candidates(const float half_len, float *ckp
   return k;
 }
 
-// l of candidate k: restart from the checkpoint, at most 15 of the reference's additions.  Left to itself the
-// compiler unrolls this loop at each of its ~20 inlined call sites (1069 of the staged kernel's 7872 instructions);
-// RMD_CANDIDATE_L_ROLLED keeps it a 4-instruction loop (A/B in profiles/r02_tune_probe.txt).
-#ifndef RMD_CANDIDATE_L_ROLLED
-#define RMD_CANDIDATE_L_ROLLED 0
-#endif
+// l of candidate k: restart from the checkpoint, at most 15 of the reference's additions.  Kept a rolled loop:
+// unrolled at each of its ~20 inlined call sites it made up 1069 of the staged kernel's 7872 instructions and
+// was no faster (profiles/r02_tune_probe.txt).
 __device__ __forceinline__ float candidate_l(const float *ckpt, const int k)
 {
   float l = ckpt[k / L_CHECKPOINT_STEP];
-#if RMD_CANDIDATE_L_ROLLED
 #pragma unroll 1
-#endif
   for(int t = 0; t < (k & (L_CHECKPOINT_STEP - 1)); ++t) l += RMD_EPIPOLAR_STEP;
   return l;
 }

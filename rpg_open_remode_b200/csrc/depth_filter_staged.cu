@@ -386,7 +386,7 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       const int reserved = (int)atomicAdd(P.counts_next + 2, (unsigned int)(znext - 1));
       znext = 1 + max(0, min(znext - 1, P.helper_cap - reserved));   // what fits in the list
     }
-    if(znext == 1 && n_active <= P.warp_tile_max_seeds && S.centroid[2] <= WARP_TILE_MAX_CANDS)
+    if(znext == 1 && n_active <= P.warp_tile_max_seeds && S.centroid[2] <= P.warp_tile_max_cands)
     {
       P.sparse_next[atomicAdd(P.counts_next + 6, 1u)] = (unsigned int)tile;   // a handful of seeds, a few dozen candidates
     }
@@ -961,7 +961,7 @@ __device__ __forceinline__ void process_warp_tile(const FilterParams &P, StagedS
   {
     atomicAdd(P.counts_next + 3, (unsigned int)items);
     atomicAdd(P.counts_next + 7, (unsigned int)n_act);
-    if(n_act <= P.warp_tile_max_seeds && total_cands <= WARP_TILE_MAX_CANDS)
+    if(n_act <= P.warp_tile_max_seeds && total_cands <= P.warp_tile_max_cands)
       P.sparse_next[atomicAdd(P.counts_next + 6, 1u)] = (unsigned int)tile;
     else if(items >= P.heavy_min_items)
       P.heavy_next[atomicAdd(P.counts_next + 0, 1u)] = (unsigned int)tile | (1u << 26);

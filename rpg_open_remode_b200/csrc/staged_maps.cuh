@@ -23,8 +23,8 @@ constexpr int SPLIT_MAX = 16;            // at most this many CTAs share one bus
 constexpr int HELPER_CAP = 1024;         // most helper CTAs per frame (work list capacity = tiles + this)
 constexpr int SPLIT_MIN_ITEMS = 512;     // tiles below this are never split
 constexpr int SPLIT_ITEMS_PER_CTA = 384; // a helper CTA must be worth its fixed cost: at least this many items each (tools/tune_probe.py)
-constexpr int HEAVY_MIN_ITEMS = 32;      // tiles with at least this many items go to the front of the work list
-constexpr int SPLIT_AVG_PCT = 100;       // ... or this percentage of the frame's items per resident-CTA slot, if larger
+constexpr int HEAVY_MIN_ITEMS = 128;     // tiles with at least this many items go to the front of the work list
+constexpr int SPLIT_AVG_PCT = 50;        // ... or this percentage of the frame's items per resident-CTA slot, if larger
 constexpr int SPARSE_MAX_SEEDS = 16;     // tiles with at most this many seeds to update skip staging
 constexpr int WARP_TILE_MAX_SEEDS = 8;   // ... and with at most this many (and WARP_TILE_MAX_CANDS candidates) are done by one warp
 constexpr int WARP_TILE_MAX_CANDS = 64;
