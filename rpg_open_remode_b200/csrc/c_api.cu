@@ -167,7 +167,6 @@ struct rmd_seeds
   int ctas_per_sm;             // RMD_OPT_TUNE_CTAS_PER_SM: 0 automatic, 2, 3
   unsigned long long *tile_keys;
   unsigned int *tile_arrivals;
-  unsigned int *strip_hint;    // [n_tiles] last frame's strip geometry per tile (strip prefetch, depth_filter_staged.cu)
   unsigned int *heavy_list[3], *light_list[3], *sparse_list[3];  // work lists of frame f in [f % 3] (written during frame f - 1)
   unsigned int *work_counts;   // 3 rotating slots of 8: {heavy, light, helpers, items, tiles listed, listers done, -, -}
   unsigned int *cursor;        // STAGED_CURSOR_WORDS: work cursors, CTAs out of work, error flag (staged_maps.cuh)
@@ -190,7 +189,7 @@ struct rmd_seeds
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  int tune[12];                // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds, grid_ctas, (ctas_per_sm: own field), warp_tile_max_cands, strip_prefetch
+  int tune[11];                // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds, grid_ctas, (ctas_per_sm: own field), warp_tile_max_cands
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
   // lens undistortion of 8-bit frames (ingest.cuh); maps are null until init_undistortion_map
   short2 *undist_xy; uint16_t *undist_frac;
@@ -258,7 +257,6 @@ int seeds_alloc(rmd_seeds *s)
     }
     RMD_CUDA_TRY(cudaMalloc(&s->tile_keys, sizeof(unsigned long long) * (size_t)s->n_tiles * staged::NPIX));
     RMD_CUDA_TRY(cudaMalloc(&s->tile_arrivals, sizeof(unsigned int) * (size_t)s->n_tiles));
-    RMD_CUDA_TRY(cudaMalloc(&s->strip_hint, sizeof(unsigned int) * (size_t)s->n_tiles));
     s->tiles_x = (w + staged::TILE_W - 1) / staged::TILE_W;
     for(int i = 0; i < 3; ++i)
     {
@@ -303,7 +301,7 @@ void seeds_free(rmd_seeds *s)
   cudaFree(s->dense_tmp);
   cudaFree(s->counters);
   cudaFree(s->timeline);
-  cudaFree(s->tile_keys); cudaFree(s->tile_arrivals); cudaFree(s->strip_hint);
+  cudaFree(s->tile_keys); cudaFree(s->tile_arrivals);
   for(int i = 0; i < 3; ++i) { cudaFree(s->heavy_list[i]); cudaFree(s->light_list[i]); cudaFree(s->sparse_list[i]); }
   cudaFree(s->work_counts);
   cudaFree(s->cursor);
@@ -386,7 +384,6 @@ int finish_set_reference(rmd_seeds *s, const float *T_curr_world, float min_dept
   // the first staged frame of a keyframe starts from the full work list; keys hold "no match"
   s->worklist_valid = false;
   RMD_CUDA_TRY(cudaMemsetAsync(s->tile_arrivals, 0, sizeof(unsigned int) * (size_t)s->n_tiles, s->stream));
-  RMD_CUDA_TRY(cudaMemsetAsync(s->strip_hint, 0, sizeof(unsigned int) * (size_t)s->n_tiles, s->stream));
   RMD_CUDA_TRY(cudaMemsetAsync(s->cursor, 0, STAGED_CURSOR_WORDS * sizeof(unsigned int), s->stream));
   RMD_CUDA_TRY(cudaMemsetAsync(s->chain_state, 0, sizeof(unsigned int) * (size_t)(s->n_tiles + 1), s->stream));   // frame numbering restarts
   RMD_CUDA_TRY(launch_fill_u64(s->tile_keys, (size_t)s->n_tiles * staged::NPIX, 0x407FFFFF00000000ull, s->stream));
@@ -458,7 +455,6 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.cta_slots = s->cta_slots[P.ctas_per_sm - 2];
     P.tile_keys = s->tile_keys;
     P.tile_arrivals = s->tile_arrivals;
-    P.strip_hint = s->tune[11] ? s->strip_hint : NULL;
     P.n_tiles = s->n_tiles; P.tiles_x = s->tiles_x; P.helper_cap = staged::HELPER_CAP;
     P.heavy_min_items = s->tune[4]; P.split_avg_pct = s->tune[5]; P.pdl = s->tune[6];
     P.heavy_cur = s->heavy_list[f % 3]; P.heavy_next = s->heavy_list[(f + 1) % 3];
@@ -866,7 +862,6 @@ int rmd_seeds_create(int width, int height, float fx, float fy, float cx, float 
   s->tune[4] = staged::HEAVY_MIN_ITEMS; s->tune[5] = staged::SPLIT_AVG_PCT; s->tune[6] = 1;
   s->tune[7] = staged::WARP_TILE_MAX_SEEDS;
   s->tune[10] = staged::WARP_TILE_MAX_CANDS;
-  s->tune[11] = 1;
   s->variant = 0;   // staged (the fast path) unless RMD_OPT_KERNEL_VARIANT says otherwise
   s->chain_frames = 1;   // chaining is opt-in: with the 128-register kernel it no longer pays (profiles/r02_occupancy_ab.txt)
   s->seed_mode_pct = 0;   // off by default: measured slower than the tile organisation on the bench workloads
@@ -949,10 +944,8 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
   case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT: case RMD_OPT_TUNE_PDL:
   case RMD_OPT_TUNE_WARP_TILE_SEEDS: case RMD_OPT_TUNE_GRID_CTAS: case RMD_OPT_TUNE_WARP_TILE_CANDS:
-  case RMD_OPT_TUNE_STRIP_PREFETCH:
     RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL ||
-                           option == RMD_OPT_TUNE_WARP_TILE_SEEDS || option == RMD_OPT_TUNE_GRID_CTAS ||
-                           option == RMD_OPT_TUNE_STRIP_PREFETCH) ? 0 : 1) && value <= 65535, "tuning value out of range");
+                           option == RMD_OPT_TUNE_WARP_TILE_SEEDS || option == RMD_OPT_TUNE_GRID_CTAS) ? 0 : 1) && value <= 65535, "tuning value out of range");
     RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= 32, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..32");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;

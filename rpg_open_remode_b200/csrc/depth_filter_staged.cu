@@ -83,7 +83,6 @@ struct __align__(128) StagedSmem
   int bbox[4];       // xmin, ymin, xmax, ymax over all segments of the CTA
   int centroid[3];   // sum of x * w, y * w, w over the seeds (w = accepted candidates, x/y = middle of their range)
   int strip_ox, strip_oy, strip_w, strip_rows;
-  int prefetched;      // the strip was requested from last frame's geometry before classification (process_tile)
   int is_last;
   unsigned int fetch;                  // index of the work-list entry this CTA processes next (persistent loop)
   unsigned int fetch_heavy, fetch_light, fetch_sparse;  // chain mode: the frame's list sizes, read BEFORE the index was drawn
@@ -219,15 +218,6 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     stamps[0] = gt;
   }
 
-  // Strip prefetch.  The strip is only a cache of the current frame (a candidate outside it reads global
-  // memory, same value), so its position never changes a result -- and it hardly moves from frame to frame.
-  // The tile's lead CTA left last frame's geometry in strip_hint: thread 0 requests the reference tile and
-  // THAT strip as soon as the classification loads are under way, and the TMA round trip (~2 us) runs under
-  // classification and search set-up instead of after them.
-  unsigned int hint = 0u;
-  if(tid == 0 && P.strip_hint)
-    hint = __ldcg(P.strip_hint + tile);
-
   // ---- 0. classification
   bool active = false, converged = false;
   int prev = RMD_BORDER, state = RMD_BORDER;
@@ -249,21 +239,6 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
   }
   if(tid == 0)
   {
-    S.prefetched = 0;
-    if(hint >> 31)
-    {
-      // hint = valid << 31 | rows/8 << 24 | width index << 22 | oy << 10 | ox/4
-      const int ox = (int)(hint & 0x3ffu) * 4, oy = (int)((hint >> 10) & 0xfffu), wi = (int)((hint >> 22) & 3u);
-      const int rows = (int)((hint >> 24) & 0x7fu) * STRIP_BOX_ROWS, sw = strip_width(wi);
-      S.strip_ox = ox; S.strip_oy = oy; S.strip_w = sw; S.strip_rows = rows;
-      S.prefetched = 1;
-      const unsigned int ref_bytes = REF_BOX_W * ref_box_h(PS) * (unsigned int)sizeof(float);
-      mbar_expect_tx(&S.mbar, ref_bytes + (unsigned int)(rows * sw) * (unsigned int)sizeof(float));
-      tma_load_2d(S.ref, &M.ref, x0 - REF_ORIGIN_X, y0 - PS / 2, &S.mbar);
-      const CUtensorMap *cm = &M.curr[wi];
-      for(int r = 0; r < rows; r += STRIP_BOX_ROWS)
-        tma_load_2d(S.strip + r * sw, cm, ox, oy + r, &S.mbar);
-    }
     S.bbox[0] = INT_MAX; S.bbox[1] = INT_MAX; S.bbox[2] = INT_MIN; S.bbox[3] = INT_MIN;
     S.items_acc = 0;
     S.n_levels = 0;
@@ -279,13 +254,6 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     // seeds are counted once in the retired total instead of every frame.
     const bool pending = inside && !(state == RMD_BORDER || state == RMD_CONVERGED || state == RMD_DIVERGED);
     const int any_pending = __syncthreads_or(pending);
-    if(S.prefetched)
-    {
-      mbar_wait(&S.mbar, mbar_phase);      // the shared memory must not be reused under a load in flight
-      mbar_phase ^= 1u;
-      if(lead && tid == 0)
-        P.strip_hint[tile] = 0u;
-    }
     if(lead)
     {
       if(lane == 0 && conv_ballot)
@@ -394,7 +362,6 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
   __syncthreads();
 
   RMD_STAMP(2);
-  bool to_warp_tile = false;    // (thread 0 of the lead CTA) listed as a warp tile: no strip next frame
   if(lead && tid == 0)
   {
     // this tile's entries in the NEXT frame's work list
@@ -422,7 +389,6 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
     if(znext == 1 && n_active <= P.warp_tile_max_seeds && S.centroid[2] <= P.warp_tile_max_cands)
     {
       P.sparse_next[atomicAdd(P.counts_next + 6, 1u)] = (unsigned int)tile;   // a handful of seeds, a few dozen candidates
-      to_warp_tile = true;
     }
     else if(znext > 1 || items >= P.heavy_min_items)
     {
@@ -448,13 +414,6 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
   if(stamps && tid == 0) stamps[13] = zeff | (sparse ? 256 : 0);
   if(sparse)
   {
-    if(S.prefetched)
-    {
-      mbar_wait(&S.mbar, mbar_phase);      // requested before the tile turned out to be sparse: let it land
-      mbar_phase ^= 1u;
-    }
-    if(lead && tid == 0 && P.strip_hint)
-      P.strip_hint[tile] = 0u;
     int seen = 0;
     for(int r = 0; r < TILE_H; ++r)
     {
@@ -542,27 +501,18 @@ __device__ __forceinline__ void process_tile(const FilterParams &P, const Staged
       ox = (bw <= sw) ? xmin_a : (min(max(cx - sw / 2, xmin_a), xmax + 1 - sw + 3) & ~3);
       oy = (want_rows <= max_rows) ? ymin : min(max(cy - rows / 2, ymin), ymax + 1 - rows);
     }
-    // what the NEXT frame requests before it has classified anything (0: nothing)
-    if(lead && P.strip_hint)
-      P.strip_hint[tile] = (rows > 0 && !to_warp_tile)
-                               ? (0x80000000u | ((unsigned int)(rows / STRIP_BOX_ROWS) << 24) | ((unsigned int)wi << 22) |
-                                  ((unsigned int)oy << 10) | (unsigned int)(ox >> 2))
-                               : 0u;
+    S.strip_ox = ox; S.strip_oy = oy; S.strip_w = sw; S.strip_rows = rows;
     if(stamps)
     {
       stamps[10] = (long long)max(0, xmax - xmin + 1) | ((long long)max(0, ymax - ymin + 1) << 16);
-      stamps[11] = (long long)sw | ((long long)rows << 16) | ((long long)S.prefetched << 32);
+      stamps[11] = (long long)sw | ((long long)rows << 16);
     }
-    if(!S.prefetched)
-    {
-      S.strip_ox = ox; S.strip_oy = oy; S.strip_w = sw; S.strip_rows = rows;
-      const unsigned int ref_bytes = REF_BOX_W * ref_box_h(PS) * (unsigned int)sizeof(float);
-      mbar_expect_tx(&S.mbar, ref_bytes + (unsigned int)(rows * sw) * (unsigned int)sizeof(float));
-      tma_load_2d(S.ref, &M.ref, x0 - REF_ORIGIN_X, y0 - PS / 2, &S.mbar);
-      const CUtensorMap *cm = &M.curr[wi];
-      for(int r = 0; r < rows; r += STRIP_BOX_ROWS)
-        tma_load_2d(S.strip + r * sw, cm, ox, oy + r, &S.mbar);
-    }
+    const unsigned int ref_bytes = REF_BOX_W * ref_box_h(PS) * (unsigned int)sizeof(float);
+    mbar_expect_tx(&S.mbar, ref_bytes + (unsigned int)(rows * sw) * (unsigned int)sizeof(float));
+    tma_load_2d(S.ref, &M.ref, x0 - REF_ORIGIN_X, y0 - PS / 2, &S.mbar);
+    const CUtensorMap *cm = &M.curr[wi];
+    for(int r = 0; r < rows; r += STRIP_BOX_ROWS)
+      tma_load_2d(S.strip + r * sw, cm, ox, oy + r, &S.mbar);
   }
 
   // ---- 3. balanced NCC search: one chunk-major work list for the whole tile

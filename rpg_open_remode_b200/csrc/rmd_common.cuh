@@ -110,7 +110,6 @@ struct FilterParams
   int cta_slots;                         // resident CTAs of the whole GPU (SMs x CTAs per SM)
   unsigned long long *tile_keys;         // [tiles][256] partial arg-max keys of split tiles
   unsigned int *tile_arrivals;           // [tiles] CTAs of a split tile that finished searching
-  unsigned int *strip_hint;              // [tiles] geometry of the strip the tile staged in the previous frame (0: none), depth_filter_staged.cu
   int n_tiles, tiles_x;                  // tile grid of the image
   // Work list of this frame, written by the lead CTAs of the previous frame.
   // Entry = tile | share << 20 | zeff << 26.  CTA b takes heavy_cur[b], then

@@ -56,7 +56,7 @@ for k in range(1, 131):
                       f"seeds {t[i,12]} zeff {t[i,13] & 255} sparse {(t[i,13] >> 8) & 1} cands strip {t[i,8]} global {t[i,9]} "
                       f"warp passes strip {(t[i,13] >> 16) & 0xffffff} global {t[i,13] >> 40} rounds {t[i,14] >> 40} "
                       f"decode cyc/round {(t[i,14] & ((1 << 40) - 1)) / max(1, t[i,14] >> 40):.0f} cand cyc/round {t[i,15] / max(1, t[i,14] >> 40):.0f} "
-                      f"bbox {t[i,10] & 0xffff}x{t[i,10] >> 16} strip {t[i,11] & 0xffff}x{(t[i,11] >> 16) & 0xffff} prefetched {t[i,11] >> 32}")
+                      f"bbox {t[i,10] & 0xffff}x{t[i,10] >> 16} strip {t[i,11] & 0xffff}x{t[i,11] >> 16}")
             print(f"   candidates scored from strip {t[:,8].sum()}, from global (fallback) {t[:,9].sum()}; sparse tiles {((t[:,13] >> 8) & 1).sum()}, split tiles {((t[:,13] & 255) > 1).sum()}")
             inact = ~act
             if inact.any():
