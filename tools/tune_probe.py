@@ -42,7 +42,7 @@ def run(cfg):
 
 # (split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_seeds,
 #  chain_frames, seed_mode_pct[, grid_ctas[, ctas_per_sm]])
-BASE = (16, 512, 384, 16, 32, 100, 1, 8)
+BASE = (16, 512, 384, 16, 128, 50, 1, 8)
 CONFIGS = [BASE + (1, 0, 0, 2), BASE + (8, 0, 0, 2), BASE + (1, 0, 0, 3), BASE + (8, 0, 0, 3)]
 if len(sys.argv) > 1:
     CONFIGS = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
