@@ -180,11 +180,15 @@ int rmd_seeds_update_u8(rmd_seeds_t *s, const uint8_t *host_img,
 /* Several live reference keyframes against one incoming frame (SURVEY.md 8f
  * row 2; the reference node keeps a single rmd::Depthmap and re-keyframes,
  * src/depthmap_node.cpp:125-157).  The frame is staged and uploaded ONCE
- * (through handles[0]) and every handle's fused kernel is enqueued on its own
- * stream, so the kernels of different keyframes overlap on the GPU -- steady
- * frames of one keyframe leave most issue slots idle.  Same
- * result as calling rmd_seeds_update[_u8] on each handle.  All handles must
- * have the same image size and device and a reference frame. */
+ * (through handles[0]) and the keyframes are updated by ONE launch per group
+ * of up to 8 (on handles[0]'s stream; the other handles' streams wait for
+ * it): the launch's work list is the concatenation of the keyframes' lists,
+ * so their dependent chains interleave from the first cycle -- steady frames
+ * of one keyframe leave most issue slots idle.  Handles on
+ * the direct variant or with another patch size are enqueued one by one.
+ * Same result, bit for bit, as calling rmd_seeds_update[_u8] on each handle.
+ * All handles must have the same image size and device and a reference
+ * frame; at most 64 per call. */
 int rmd_seeds_update_many(rmd_seeds_t *const *handles, int n, const float *host_img,
                           const float *T_curr_world);
 int rmd_seeds_update_many_u8(rmd_seeds_t *const *handles, int n, const uint8_t *host_img,
