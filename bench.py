@@ -247,11 +247,15 @@ def ncu_capture(patch):
         traffic = {"heavy_frame": t["heavy"], "steady_frame": t["steady"], "source": src}
         m = j["metrics"]
         key = "smsp__issue_active.avg.pct_of_peak_sustained_active"
-        bound = {"bound": "instruction issue (search-heavy frames) / dependent-chain latency (steady frames)",
+        dur = m["gpu__time_duration.sum"]
+        to_us = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6}
+        bound = {"bound": "dependency latency at 16 warps per SM (search-heavy frames) / critical path of the busiest "
+                          "CTA (steady frames)",
                  "heavy_frame_issue_slots_pct": float(m[key]["heavy"]),
                  "steady_frame_issue_slots_pct": float(m[key]["steady"]),
-                 "heavy_frame_us_under_ncu": float(m["gpu__time_duration.sum"]["heavy"]),
-                 "steady_frame_us_under_ncu": float(m["gpu__time_duration.sum"]["steady"]), "source": src}
+                 "heavy_frame_us_under_ncu": float(dur["heavy"]) * to_us.get(dur.get("unit", "us"), 1.0),
+                 "steady_frame_us_under_ncu": float(dur["steady"]) * to_us.get(dur.get("unit_steady", dur.get("unit", "us")), 1.0),
+                 "source": src}
         return traffic, bound
     except Exception:
         return None, None
@@ -462,8 +466,9 @@ def run_ours(args, rank, world, local_rank):
                     "rest_ms": float(per_launch_ms[19:].sum())},
                 "kernel_share_of_step": ncu_kernel_share(args.patch),
                 "what_bounds_it": bound,
-                "note": "search-heavy frames are instruction-issue bound (<=143 candidates x P^2 bilinear taps per "
-                        "seed), steady frames latency bound; not HBM bound: see DESIGN.md 4.1 'What bounds it'"}
+                "note": "search-heavy frames are bound by dependency latency (<=143 candidates x P^2 bilinear taps per "
+                        "seed, sums serial by bit-parity), steady frames by the critical path of the busiest CTA; not HBM "
+                        "bound: see DESIGN.md 4.1 'What bounds it'"}
 
     out = {
         "metric": args.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

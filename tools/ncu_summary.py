@@ -50,7 +50,7 @@ def main():
         if m not in heavy:
             continue
         (hv, hu), (sv, su) = heavy[m], steady[m]
-        out["metrics"][m] = {"heavy": hv, "steady": sv, "unit": hu}
+        out["metrics"][m] = {"heavy": hv, "steady": sv, "unit": hu, "unit_steady": su}
         lines.append(f"| `{m}` | {hv} {hu} | {sv} {su} |")
     for key, rep in (("heavy", heavy), ("steady", steady)):
         tot = 0.0
