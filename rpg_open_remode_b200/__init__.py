@@ -10,7 +10,7 @@ from .api import (ConvergenceStates, DepthmapDenoiser, Depthmap, DeviceImage, Im
                   FIELD_CONST_TEMPL_DENOM, FIELD_EPIPOLAR_MATCHES, FIELD_REF_IMG,
                   OPT_RECORD_MATCHES, OPT_KERNEL_VARIANT, OPT_TEX_FRAC_BITS, OPT_DEBUG_TIMELINE, OPT_PINNED_INPUT, OPT_CHAIN_FRAMES, OPT_SEED_MODE_PCT,
                   OPT_TUNE_SPLIT_MAX, OPT_TUNE_SPLIT_MIN_ITEMS, OPT_TUNE_SPLIT_ITEMS_PER_CTA,
-                  OPT_TUNE_SPARSE_MAX_SEEDS, OPT_TUNE_HEAVY_MIN_ITEMS, OPT_TUNE_SPLIT_AVG_PCT, OPT_TUNE_PDL, OPT_TUNE_WARP_TILE_SEEDS, OPT_TUNE_GRID_CTAS, OPT_TUNE_CTAS_PER_SM, OPT_TUNE_WARP_TILE_CANDS, OPT_TUNE_LIST_ORDER,
+                  OPT_TUNE_SPARSE_MAX_SEEDS, OPT_TUNE_HEAVY_MIN_ITEMS, OPT_TUNE_SPLIT_AVG_PCT, OPT_TUNE_PDL, OPT_TUNE_WARP_TILE_SEEDS, OPT_TUNE_GRID_CTAS, OPT_TUNE_CTAS_PER_SM, OPT_TUNE_WARP_TILE_CANDS,
                   VARIANT_STAGED, VARIANT_DIRECT)
 from ._native import device_count
 

@@ -44,7 +44,6 @@ OPT_TUNE_WARP_TILE_SEEDS = 17
 OPT_TUNE_GRID_CTAS = 18
 OPT_TUNE_CTAS_PER_SM = 19
 OPT_TUNE_WARP_TILE_CANDS = 20
-OPT_TUNE_LIST_ORDER = 21
 FIELD_DEBUG_TIMELINE = 100
 VARIANT_STAGED, VARIANT_DIRECT = 0, 1
 

@@ -189,7 +189,7 @@ struct rmd_seeds
   bool worklist_valid;         // false: rebuild (all tiles, image order) before the next staged launch
   bool last_staged;            // the last update ran the staged kernel (retired count applies)
   int tiles_x;
-  int tune[12];                // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds, grid_ctas, (ctas_per_sm: own field), warp_tile_max_cands, list_order
+  int tune[11];                // split_max, split_min_items, split_items_per_cta, sparse_max_seeds, heavy_min_items, split_avg_pct, pdl, warp_tile_max_seeds, grid_ctas, (ctas_per_sm: own field), warp_tile_max_cands
   ParallelCopier *copier;   // host frame -> pinned ring (created on first host update)
   // lens undistortion of 8-bit frames (ingest.cuh); maps are null until init_undistortion_map
   short2 *undist_xy; uint16_t *undist_frac;
@@ -462,7 +462,6 @@ int prepare_update(rmd_seeds *s, const float *curr, size_t curr_pitch, const flo
     P.sparse_cur = s->sparse_list[f % 3]; P.sparse_next = s->sparse_list[(f + 1) % 3];
     P.warp_tile_max_seeds = s->tune[7];
     P.warp_tile_max_cands = s->tune[10];
-    P.list_order = s->tune[11];
     P.grid_ctas = s->tune[8];
     P.counts_cur = s->work_counts + 8 * (f % 3);
     P.counts_next = s->work_counts + 8 * ((f + 1) % 3);
@@ -945,10 +944,8 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   case RMD_OPT_TUNE_SPLIT_MAX: case RMD_OPT_TUNE_SPLIT_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_ITEMS_PER_CTA:
   case RMD_OPT_TUNE_SPARSE_MAX_SEEDS: case RMD_OPT_TUNE_HEAVY_MIN_ITEMS: case RMD_OPT_TUNE_SPLIT_AVG_PCT: case RMD_OPT_TUNE_PDL:
   case RMD_OPT_TUNE_WARP_TILE_SEEDS: case RMD_OPT_TUNE_GRID_CTAS: case RMD_OPT_TUNE_WARP_TILE_CANDS:
-  case RMD_OPT_TUNE_LIST_ORDER:
     RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL ||
-                           option == RMD_OPT_TUNE_WARP_TILE_SEEDS || option == RMD_OPT_TUNE_GRID_CTAS ||
-                           option == RMD_OPT_TUNE_LIST_ORDER) ? 0 : 1) && value <= 65535, "tuning value out of range");
+                           option == RMD_OPT_TUNE_WARP_TILE_SEEDS || option == RMD_OPT_TUNE_GRID_CTAS) ? 0 : 1) && value <= 65535, "tuning value out of range");
     RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= 32, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..32");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;

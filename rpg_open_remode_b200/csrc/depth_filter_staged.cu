@@ -1086,8 +1086,7 @@ __global__ void __launch_bounds__(NTHREADS, MB) depth_filter_staged_kernel(
     }
     else
     {
-      // entry i of the concatenation: heavy lists of keyframes 0..n-1, then (order 0) their light lists and
-      // their groups of warp tiles, or (order 1) the groups of warp tiles before the light lists
+      // entry i of the concatenation: heavy lists of keyframes 0..n-1, then their light lists
       unsigned int base = 0u;
 #pragma unroll 1
       for(int k = 0; k < n_kf && kf < 0; ++k)
@@ -1097,32 +1096,21 @@ __global__ void __launch_bounds__(NTHREADS, MB) depth_filter_staged_kernel(
         if(i - base < n_heavy) { kf = k; entry = P.heavy_cur[i - base]; }
         base += n_heavy;
       }
-      const int order = B.p[0].list_order;
 #pragma unroll 1
-      for(int pass = 0; pass < 2 && kf < 0; ++pass)
+      for(int k = 0; k < n_kf && kf < 0; ++k)
       {
-        if((pass == 0) == (order == 0))
-        {
+        const FilterParams &P = B.p[K == 1 ? 0 : k];
+        const unsigned int n_light = P.counts_cur[1];
+        if(i - base < n_light) { kf = k; entry = P.light_cur[i - base]; }
+        base += n_light;
+      }
 #pragma unroll 1
-          for(int k = 0; k < n_kf && kf < 0; ++k)
-          {
-            const FilterParams &P = B.p[K == 1 ? 0 : k];
-            const unsigned int n_light = P.counts_cur[1];
-            if(i - base < n_light) { kf = k; entry = P.light_cur[i - base]; }
-            base += n_light;
-          }
-        }
-        else
-        {
-#pragma unroll 1
-          for(int k = 0; k < n_kf && kf < 0; ++k)
-          {
-            const FilterParams &P = B.p[K == 1 ? 0 : k];
-            const unsigned int ns = P.counts_cur[6], groups = (ns + NWARPS - 1) / NWARPS;
-            if(i - base < groups) { kf = k; sparse_group = (int)(i - base); n_sparse = ns; }
-            base += groups;
-          }
-        }
+      for(int k = 0; k < n_kf && kf < 0; ++k)
+      {
+        const FilterParams &P = B.p[K == 1 ? 0 : k];
+        const unsigned int ns = P.counts_cur[6], groups = (ns + NWARPS - 1) / NWARPS;
+        if(i - base < groups) { kf = k; sparse_group = (int)(i - base); n_sparse = ns; }
+        base += groups;
       }
       if(kf < 0)
         break;           // the lists are exhausted (uniform: every thread read the same index)

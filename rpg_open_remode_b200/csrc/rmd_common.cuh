@@ -123,7 +123,6 @@ struct FilterParams
   const unsigned int *sparse_cur;
   unsigned int *sparse_next;
   int warp_tile_max_seeds;               // 0: no warp tiles
-  int list_order;                        // 0: heavy, light, warp-tile groups; 1: heavy, warp-tile groups, light
   int warp_tile_max_cands;               // a warp tile has at most this many candidates in all
   int ctas_per_sm;                       // 5x5 staged kernel: 2 (128 registers) or 3 (80 registers) resident CTAs per SM (host side only)
   int grid_ctas;                         // 0: one CTA per resident slot; else the persistent grid's size (host side only)

@@ -20,13 +20,12 @@ g = rmd.SeedMatrix(W, H, rmd.PinholeCamera(*seq.camera), patch_side=int(os.envir
 def full(cfg):
     cfg = tuple(cfg)
     cfg = cfg + (0,) * max(0, 12 - len(cfg))
-    cfg = cfg + (64,) * max(0, 13 - len(cfg))
-    return cfg + (0,) * (14 - len(cfg))
+    return cfg + (64,) * (13 - len(cfg))
 
 
 def run(cfg):
     cfg = full(cfg)
-    for opt, val in zip((10, 11, 12, 13, 14, 15, 16, 17, 5, 6, 18, 19, 20, 21), cfg): g.setOption(opt, val)
+    for opt, val in zip((10, 11, 12, 13, 14, 15, 16, 17, 5, 6, 18, 19, 20), cfg): g.setOption(opt, val)
     best = 1e9; seg = None
     for rep in range(4):
         g.setReferenceImageDevice(d_frames[0].data_ptr(), W * 4, poses[0], dmin, dmax)
@@ -49,5 +48,5 @@ if len(sys.argv) > 1:
     CONFIGS = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 for cfg in CONFIGS:
     tot, seg = run(cfg)
-    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d pdl %d warp_tiles %d chain %d seed_pct %d grid %d ctas/sm %d wt_cands %d order %d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-end %.2f ms" %
+    print("split_max %2d min_items %4d per_cta %4d sparse %3d heavy_min %5d avg_pct %3d pdl %d warp_tiles %d chain %d seed_pct %d grid %d ctas/sm %d wt_cands %d : total %.2f ms (%.0f fps)  frames1-19 %.2f  20-99 %.2f  100-end %.2f ms" %
           (*(tuple(cfg) + (0,) * (12 - len(cfg)) if len(cfg) < 13 else tuple(cfg)), tot, (N - 1) / tot * 1e3, *seg), flush=True)
