@@ -32,6 +32,9 @@ for stage in "$@"; do
     ncu_warm)   timeout 900 ncu --cache-control none --clock-control none --section WarpStateStats --section SchedulerStats -k regex:depth_filter_staged -s 129 -c 1 $BENCH_NCU 2>&1 | grep -v "^==PROF==" | tail -n 60 > $OUT/ncu_p5_steady_warm.txt; cat $OUT/ncu_p5_steady_warm.txt ;;
     knobs3)     H="16,512,384,16,128,50,1"; T=",1,0,0,2"; for size in 640,480,200 1280,720,300; do echo "image, frames: $size"
                   RMD_PROBE_SIZE=$size timeout 600 python tools/tune_probe.py $H,8$T,64 $H,8$T,128 $H,12$T,96 $H,16$T,128 $H,16$T,256 $H,24$T,192 $H,32$T,256 $H,32$T,512 $H,0$T,64 $H,8$T,64 2>&1 | tail -n 10 | sed 's/^.*pdl 1 warp_tiles/  warp_tiles/;s/chain 1 seed_pct 0 grid 0 ctas.sm 2 //'; done ;;
+    strip_ab)   H="16,512,384,16,128,50,1,8,1,0,0,2,64"; for lib in librmd_b200.so build/librmd_b200_strip60.so build/librmd_b200_strip80.so; do echo "library $lib:"
+                  for cfg in 640,480,200,5 1280,720,300,5 1920,1080,120,7; do
+                    RMD_PROBE_SIZE=${cfg%,*} RMD_PROBE_PATCH=${cfg##*,} RMD_B200_LIB=$PWD/rpg_open_remode_b200/$lib timeout 600 python tools/tune_probe.py $H 2>&1 | tail -n 1 | sed "s/^.*wt_cands 64/  $cfg/"; done; done ;;
     occupancy_ab) for size in 640,480,200 1280,720,300; do echo "image, frames: $size"; RMD_PROBE_SIZE=$size timeout 600 python tools/tune_probe.py 2>&1 | tail -n 4; done ;;
     bench_c3)   timeout 900 python bench.py --config c3 > $OUT/bench_c3.json 2> $OUT/bench_c3.err ;;
     bench_c4)   timeout 900 python bench.py --config c4 > $OUT/bench_c4.json 2> $OUT/bench_c4.err ;;
