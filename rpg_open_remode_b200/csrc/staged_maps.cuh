@@ -19,9 +19,9 @@ constexpr int NPIX = TILE_W * TILE_H;  // seeds per CTA
 constexpr int CHUNK = 4;               // candidates per work item
 constexpr int MAX_CHUNKS = 36;         // ceil(143 / CHUNK): 100 px / 0.7 px + 1 = 143 candidates
 #ifndef RMD_STRIP_FLOATS
-#define RMD_STRIP_FLOATS 10240
+#define RMD_STRIP_FLOATS 15360
 #endif
-constexpr int STRIP_FLOATS = RMD_STRIP_FLOATS;    // current-image strip per CTA (40 KB; tools/build_variant_lib.sh for A/Bs)
+constexpr int STRIP_FLOATS = RMD_STRIP_FLOATS;    // current-image strip per CTA: 60 KB (40 KB: +1.5 %, 80 KB: -0.4 % but only 18 KB of L1 left; profiles/r02_occupancy_ab.txt)
 constexpr int SPLIT_MAX = 16;            // at most this many CTAs share one busy tile
 constexpr int HELPER_CAP = 1024;         // most helper CTAs per frame (work list capacity = tiles + this)
 constexpr int SPLIT_MIN_ITEMS = 512;     // tiles below this are never split
