@@ -12,12 +12,12 @@
 
 #include "rmd_common.cuh"
 #include "packed_f32x2.cuh"
+#include "candidate_range.cuh"
 
 namespace rmdb
 {
 
 #define RMD_MAX_EPIPOLAR_EXTENT 100.0f  // RMD_MAX_EXTENT_EPIPOLAR_SEARCH, CMakeLists.txt:53
-#define RMD_EPIPOLAR_STEP 0.7f          // src/epipolar_match.cu:88
 #define RMD_NCC_ACCEPT 0.5f             // src/epipolar_match.cu:131
 
 __device__ __forceinline__ float dot3(const float3 a, const float3 b)
@@ -109,14 +109,6 @@ __device__ __forceinline__ int classify_seed(const FilterParams &P, const float4
   return RMD_UPDATE;
 }
 
-// The epipolar search segment of one seed, src/epipolar_match.cu:60-75.
-struct EpiSegment
-{
-  float2 mean;      // projection of the depth estimate
-  float2 dir;       // unit direction of the segment
-  float half_len;   // half of min(segment length, 100 px)
-};
-
 // se3.cuh:164-168 + pinhole_camera.cuh:48-53: project(cam, T * p), roundings pinned
 __device__ __forceinline__ float2 transform_project_pinned(const Camera &cam, const Pose &T, const float3 p)
 {
@@ -162,22 +154,6 @@ __device__ __forceinline__ EpiSegment epipolar_segment(
   if(!(fabsf(len_sq) < CUDART_INF_F))
     s.half_len = CUDART_NAN_F;     // `l <= half_len` is never true: the search loop does not run
   return s;
-}
-
-// True when the candidate patch centre is outside the searchable interior,
-// src/epipolar_match.cu:91-97 (NaN coordinates pass, as there).
-template<int PS>
-__device__ __forceinline__ bool candidate_rejected(const float2 px, const int width, const int height)
-{
-  return (px.x >= (float)(width - PS)) || (px.y >= (float)(height - PS)) ||
-         (px.x < (float)PS) || (px.y < (float)PS);
-}
-
-// Candidate l of a segment: px_mean + l * epi_dir (src/epipolar_match.cu:90), one fused multiply-add per axis.
-__device__ __forceinline__ float2 candidate_px(const float mean_x, const float mean_y, const float dir_x,
-                                               const float dir_y, const float l)
-{
-  return make_float2(__fmaf_rn(l, dir_x, mean_x), __fmaf_rn(l, dir_y, mean_y));
 }
 
 // Integer origin and (optionally quantised) bilinear weights of a candidate.
