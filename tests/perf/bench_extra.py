@@ -6,7 +6,7 @@ reference's own CUDA build where it can run them:
   * reductions: countEqual / sum on 752x480
   * frame ingest: float vs 8-bit host frames through update()
 
-Prints one JSON object; tools/gpu_trip*.sh stores it under gpurun_out/ and the
+Prints one JSON object; tools/gpu_trip.sh (stage `extra`) stores it under gpurun_out/ and the
 summary lives in profiles/r01_extra_bench.md.
 """
 import json
