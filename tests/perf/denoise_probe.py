@@ -3,7 +3,7 @@ product vs the reference's own kernel (oracle/_ref) on the same seed state (GPU 
 `--once`: a single 720p / 50-iteration call (the target of the ncu capture, stage ncu_denoise)."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch
