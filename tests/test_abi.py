@@ -46,6 +46,65 @@ def test_no_cpu_fallback():
     assert "oracle_binding" not in src and "librmd_oracle" not in src
 
 
+def test_only_tests_smoke_and_bench_touch_the_checkers():
+    """oracle/ (the CPU restatement and the rebuilt reference) is test infrastructure: nothing in the package, its
+    native sources, the public headers or tools/ may import, load, link or execute it."""
+    import ast
+    import re
+    needles = re.compile(r"oracle_binding|ref_binding|librmd_oracle|librmd_ref|oracle/|/oracle\b|_ref/")
+    offenders = []
+
+    def python_hits(path):
+        tree = ast.parse(open(path).read())
+        docstrings = set()
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.Module, ast.ClassDef, ast.FunctionDef, ast.AsyncFunctionDef)) and node.body and \
+                    isinstance(node.body[0], ast.Expr) and isinstance(getattr(node.body[0], "value", None), ast.Constant):
+                docstrings.add(id(node.body[0].value))
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""] + [a.name for a in node.names]
+            elif isinstance(node, ast.Constant) and isinstance(node.value, str) and id(node) not in docstrings:
+                names = [node.value]
+            else:
+                continue
+            for n in names:
+                if needles.search(n):
+                    yield node.lineno, n
+
+    for top in ("rpg_open_remode_b200", "include", "tools"):
+        for dirpath, dirnames, filenames in os.walk(os.path.join(ROOT, top)):
+            dirnames[:] = [d for d in dirnames if d not in ("build", "__pycache__")]
+            for name in filenames:
+                path = os.path.join(dirpath, name)
+                rel = os.path.relpath(path, ROOT)
+                if name.endswith(".py"):
+                    offenders += [f"{rel}:{no}: {what[:100]}" for no, what in python_hits(path)]
+                elif name.endswith((".sh", ".cu", ".cuh", ".h", ".c", ".cpp", ".hpp")):
+                    in_block = False
+                    for no, line in enumerate(open(path, errors="replace"), 1):
+                        code = line.split("#", 1)[0] if name.endswith(".sh") else line.split("//", 1)[0]
+                        if not name.endswith(".sh"):
+                            # drop /* ... */ comments (headers cite the reference and the oracle in prose)
+                            if in_block:
+                                if "*/" not in code:
+                                    continue
+                                code = code.split("*/", 1)[1]
+                                in_block = False
+                            while "/*" in code:
+                                head, rest = code.split("/*", 1)
+                                if "*/" in rest:
+                                    code = head + rest.split("*/", 1)[1]
+                                else:
+                                    code = head
+                                    in_block = True
+                        if needles.search(code):
+                            offenders.append(f"{rel}:{no}: {line.strip()[:120]}")
+    assert not offenders, "\n".join(offenders)
+
+
 def test_se3_mirror_matches_oracle_host_math():
     """rmd::SE3 host arithmetic (se3.cuh) as mirrored in api.SE3 == oracle's."""
     import oracle_binding as ob
