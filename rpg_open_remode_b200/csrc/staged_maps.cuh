@@ -39,8 +39,11 @@ constexpr int REF_ORIGIN_X = 4;        // the reference box starts at x0 - 4 (16
 constexpr int NUM_WIDTHS = 4;
 __host__ __device__ constexpr int strip_width(int i)
 {
-  // multiples of 32 floats: with one warp per pixel row, lanes read consecutive
-  // columns, so bank = column mod 32 is conflict-free whatever row a lane is on
+  // multiples of 32 floats, so bank = column mod 32 whatever row a lane is on: the 32 lanes of a round score the
+  // candidates of 32 neighbouring pixels, i.e. (nearly) consecutive columns.  Not conflict-free in practice: as soon
+  // as the two views differ in scale the 32 blocks span more than 32 columns and two lanes share a bank -- ncu counts
+  // 1.9 wavefronts per LDS of the NCC on search-heavy frames (profiles/r02_ncu_staged.md); TMA's swizzle modes
+  // only apply to rows of <= 128 bytes, the strip's are 256..640.
   return i == 0 ? 64 : (i == 1 ? 96 : (i == 2 ? 128 : 160));
 }
 __host__ __device__ constexpr int ref_box_h(int patch) { return TILE_H + patch - 1; }
