@@ -122,10 +122,10 @@ enum rmd_seeds_option {
   RMD_OPT_TUNE_HEAVY_MIN_ITEMS = 14,      /* tiles with at least this many items are dispatched first (128) */
   RMD_OPT_TUNE_SPLIT_AVG_PCT = 15,        /* target items per CTA of a split tile, in % of the frame's items per resident CTA slot (50) */
   RMD_OPT_TUNE_PDL = 16,           /* 1 (default): programmatic dependent launch of consecutive frames */
-  RMD_OPT_TUNE_WARP_TILE_SEEDS = 17, /* tiles with at most this many seeds to update (and a few dozen candidates) are processed by one warp, eight tiles per CTA (8; 0 = off; at most 32) */
+  RMD_OPT_TUNE_WARP_TILE_SEEDS = 17, /* tiles with at most this many seeds to update (and a few dozen candidates) are processed by one warp, eight tiles per CTA (8 = the most; 0 = off) */
   RMD_OPT_TUNE_GRID_CTAS = 18,      /* size of the persistent grid (0, the default: one CTA per resident slot, SMs x occupancy) */
   RMD_OPT_TUNE_CTAS_PER_SM = 19,    /* 5x5 staged kernel: the 128-register build (2, = 0, the default) or the 80-register build (3; sized for 3 CTAs per SM, of which two fit next to the 60 KB strips) */
-  RMD_OPT_TUNE_WARP_TILE_CANDS = 20  /* ... and at most this many candidates in all (64) */
+  RMD_OPT_TUNE_WARP_TILE_CANDS = 20  /* ... and at most this many candidates in all (64 = the most) */
 };
 
 typedef struct rmd_seeds rmd_seeds_t;

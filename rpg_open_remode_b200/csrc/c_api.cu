@@ -946,7 +946,10 @@ int rmd_seeds_set_option(rmd_seeds_t *s, int option, int value)
   case RMD_OPT_TUNE_WARP_TILE_SEEDS: case RMD_OPT_TUNE_GRID_CTAS: case RMD_OPT_TUNE_WARP_TILE_CANDS:
     RMD_REQUIRE(value >= ((option == RMD_OPT_TUNE_SPARSE_MAX_SEEDS || option == RMD_OPT_TUNE_PDL ||
                            option == RMD_OPT_TUNE_WARP_TILE_SEEDS || option == RMD_OPT_TUNE_GRID_CTAS) ? 0 : 1) && value <= 65535, "tuning value out of range");
-    RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= 32, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..32");
+    // (larger warp tiles ran in the A/B of profiles/r02_tune_probe.txt -- slower -- but only these ranges are
+    // covered by the bit-equality tests)
+    RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_SEEDS || value <= staged::WARP_TILE_MAX_SEEDS, "RMD_OPT_TUNE_WARP_TILE_SEEDS: 0..8");
+    RMD_REQUIRE(option != RMD_OPT_TUNE_WARP_TILE_CANDS || value <= staged::WARP_TILE_MAX_CANDS, "RMD_OPT_TUNE_WARP_TILE_CANDS: 1..64");
     RMD_REQUIRE(option != RMD_OPT_TUNE_SPLIT_MAX || value <= 32, "RMD_OPT_TUNE_SPLIT_MAX: 1..32");
     s->tune[option - RMD_OPT_TUNE_SPLIT_MAX] = value;
     return 0;
