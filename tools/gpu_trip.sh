@@ -57,7 +57,7 @@ for stage in "$@"; do
                 B="16,512,384,16,128,50,1,8,1,0,0,2,64"
                 timeout 900 python tools/tune_probe.py $B ${B/,16,128,50,/,32,128,50,} ${B/,16,128,50,/,64,128,50,} ${B/16,512,384,/16,256,128,} ${B/16,512,384,/16,384,256,} \
                   ${B/,128,50,/,32,50,} ${B/,128,50,/,64,50,} ${B/,128,50,/,256,50,} ${B/,128,50,/,128,100,} ${B/,128,50,/,128,200,} \
-                  ${B/,1,8,1,0,0,2,64/,1,0,1,0,0,2,64} ${B/,1,8,1,0,0,2,64/,1,8,1,0,0,2,128} ${B/,1,8,1,0,0,2,64/,1,16,1,0,0,2,128} $B 2>&1 | tail -n 14 ;;
+                  ${B/,1,8,1,0,0,2,64/,1,0,1,0,0,2,64} ${B/,1,8,1,0,0,2,64/,1,4,1,0,0,2,64} ${B/,1,8,1,0,0,2,64/,1,8,1,0,0,2,32} $B 2>&1 | tail -n 14 ;;
     seed_mode)  for pct in 0 15 25 40; do timeout 600 python bench.py --seed-mode-pct $pct --no-cpu-baseline --steps 10 > $OUT/bench_c2_seed$pct.json 2> $OUT/bench_c2_seed$pct.err
                   python -c "import json; d=json.loads(open('$OUT/bench_c2_seed$pct.json').read()); print('seed pct $pct: value', round(d['value']), 'ms', round(d['ms_per_step'], 2), 'e2e', round(d['e2e']['value']), round(d['e2e']['ms_per_step'], 2))"; done ;;
     chain_ab)   for n in 1 8; do timeout 900 python bench.py --config c4 --frames 120 --no-e2e --no-cpu-baseline --chain-frames $n > $OUT/bench_c4_chain$n.json 2> $OUT/bench_c4_chain$n.err
