@@ -233,15 +233,19 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_capture(patch):
+def ncu_capture(patch, algo_bytes=None):
     """The committed `ncu --set full` capture of the dominant kernel (heavy and steady frame): DRAM traffic
-    per launch and the issue-slot utilisation that actually bounds it.  Never measured under the timed run."""
+    per launch and the issue-slot utilisation that actually bounds it.  Never measured under the timed run.
+    Captures exist for the VGA 5x5 and the 1080p 7x7 workloads: for any other image size the traffic is not
+    reported (None) rather than borrowed from a capture of different launches."""
     path = _profile("ncu_staged.json") if patch == 5 else _profile("ncu_staged_p7.json")
     if not path:
         return None, None
     try:
         with open(path) as f:
             j = json.load(f)
+        if algo_bytes is not None and abs(float(j.get("algorithmic_bytes_per_launch", 0.0)) - float(algo_bytes)) > 0.5:
+            return None, None
         t = j["traffic_bytes_per_launch"]
         src = os.path.relpath(path, ROOT)
         traffic = {"heavy_frame": t["heavy"], "steady_frame": t["steady"], "source": src}
@@ -449,7 +453,7 @@ def run_ours(args, rank, world, local_rank):
     algo_bytes = BYTES_PER_PIXEL_FUSED * W * H
     peak, peak_src = peaks()
     achieved = algo_bytes / avg_launch_s / 1e9
-    traffic, bound = ncu_capture(args.patch)
+    traffic, bound = ncu_capture(args.patch, algo_bytes)
     roofline = {"bound": "hbm", "kernel": "depth_filter_%s_kernel<%d>" % (variant, args.patch),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": (traffic or {}).get("heavy_frame"),
